@@ -1,0 +1,133 @@
+/* ilqg_cuda.cu -- the CUDA layer under the C host code: kernel instantiation for ONE generated problem
+ * (-DILQG_PROBLEM_HEADER=... -DILQG_PROBLEM_STRUCT=... -DFULL_DDP=0|1, like the reference builds one mex per
+ * problem and FULL_DDP setting, make_iLQG.m:65-86) and thin extern "C" launch / memory wrappers.
+ * No solver logic lives here; see ilqg_host.c.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false. */
+#include <cstdio>
+#include <cstring>
+#include "ilqg_kernels.cuh"
+#include ILQG_PROBLEM_HEADER
+#include "ilqg_cuda.h"
+
+#ifndef FULL_DDP
+#define FULL_DDP 1
+#endif
+
+using P = ILQG_PROBLEM_STRUCT;
+using namespace ilqg;
+
+static thread_local char g_err[256] = "";
+
+static int check(cudaError_t e, const char *what)
+{
+    if (e == cudaSuccess) return 0;
+    snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
+    return -1;
+}
+
+static ParamBlock<P> make_pb(const double *params)
+{
+    ParamBlock<P> pb;
+    memset(&pb, 0, sizeof pb);
+    memcpy(pb.v, params, sizeof(double) * P::NPF_USED);
+    return pb;
+}
+
+extern "C" {
+
+const char *ilqgk_last_error(void) { return g_err; }
+
+void ilqgk_dims(ilqgk_dims_t *d)
+{
+    d->nx = P::NX; d->nu = P::NU; d->nqxx = P::NQXX; d->nquu = P::NQUU; d->nqxu = P::NQXU;
+    d->nv1 = P::NV1; d->nv2 = P::NV2; d->npf = P::NPF_USED; d->nkp = P::NKP;
+    d->n_mu_r = P::N_MU_R; d->n_mu_f = P::N_MU_F; d->n_mu_le = P::N_MU_LE; d->n_mu_fe = P::N_MU_FE;
+    d->full_ddp = FULL_DDP; d->has_hx = P::HAS_HX ? 1 : 0;
+}
+const char *ilqgk_problem_name(void) { return P::name(); }
+int ilqgk_param_count(void) { return P::param_count(); }
+const char *ilqgk_param_name(int i) { return P::param_name(i); }
+int ilqgk_param_size(int i) { return P::param_size(i); }
+
+int ilqgk_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+int ilqgk_set_device(int dev) { return check(cudaSetDevice(dev), "cudaSetDevice"); }
+int ilqgk_malloc(void **p, size_t bytes) { return check(cudaMalloc(p, bytes ? bytes : 8), "cudaMalloc"); }
+int ilqgk_free(void *p) { return p ? check(cudaFree(p), "cudaFree") : 0; }
+int ilqgk_host_alloc(void **p, size_t bytes) { return check(cudaHostAlloc(p, bytes ? bytes : 8, cudaHostAllocDefault), "cudaHostAlloc"); }
+int ilqgk_host_free(void *p) { return p ? check(cudaFreeHost(p), "cudaFreeHost") : 0; }
+int ilqgk_memset(void *p, int v, size_t bytes, void *stream) { return check(cudaMemsetAsync(p, v, bytes, (cudaStream_t)stream), "cudaMemsetAsync"); }
+int ilqgk_h2d(void *dst, const void *src, size_t bytes, void *stream) { return check(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream), "H2D"); }
+int ilqgk_d2h(void *dst, const void *src, size_t bytes, void *stream) { return check(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream), "D2H"); }
+int ilqgk_stream_create(void **s) { cudaStream_t st; int r = check(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "cudaStreamCreate"); *s = (void *)st; return r; }
+int ilqgk_stream_destroy(void *s) { return check(cudaStreamDestroy((cudaStream_t)s), "cudaStreamDestroy"); }
+int ilqgk_stream_sync(void *s) { return check(cudaStreamSynchronize((cudaStream_t)s), "cudaStreamSynchronize"); }
+int ilqgk_event_create(void **e) { cudaEvent_t ev; int r = check(cudaEventCreate(&ev), "cudaEventCreate"); *e = (void *)ev; return r; }
+int ilqgk_event_destroy(void *e) { return check(cudaEventDestroy((cudaEvent_t)e), "cudaEventDestroy"); }
+int ilqgk_event_record(void *e, void *s) { return check(cudaEventRecord((cudaEvent_t)e, (cudaStream_t)s), "cudaEventRecord"); }
+int ilqgk_event_elapsed(void *a, void *b, float *ms) { return check(cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b), "cudaEventElapsedTime"); }
+
+static inline unsigned nblk(int n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+int ilqgk_launch_init(const ilqg_work *w, const ilqg_opts *o, const double *params, void *stream)
+{
+    k_init<P><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, make_pb(params));
+    return check(cudaGetLastError(), "k_init");
+}
+
+int ilqgk_launch_derivs(const ilqg_work *w, const double *params, void *stream)
+{
+    dim3 grid(nblk(w->B, DV_BLOCK), (unsigned)(w->T + 1));
+    k_derivs<P, FULL_DDP != 0><<<grid, DV_BLOCK, 0, (cudaStream_t)stream>>>(*w, make_pb(params));
+    return check(cudaGetLastError(), "k_derivs");
+}
+
+int ilqgk_launch_backpass(const ilqg_work *w, const ilqg_opts *o, const double *params, int iter, void *stream)
+{
+    k_backpass<P, FULL_DDP != 0><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, make_pb(params), iter);
+    return check(cudaGetLastError(), "k_backpass");
+}
+
+int ilqgk_launch_linesearch(const ilqg_work *w, const ilqg_opts *o, const double *params, int iter, void *stream)
+{
+    k_linesearch<P><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, make_pb(params), iter);
+    return check(cudaGetLastError(), "k_linesearch");
+}
+
+int ilqgk_launch_post(const ilqg_work *w, const ilqg_opts *o, const double *params, void *stream)
+{
+    if (P::N_MU_R + P::N_MU_F == 0) return 0;   /* cost does not depend on multipliers/penalties: nothing to redo */
+    k_post<P><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, make_pb(params));
+    return check(cudaGetLastError(), "k_post");
+}
+
+int ilqgk_has_post(void) { return (P::N_MU_R + P::N_MU_F) > 0; }
+
+int ilqgk_launch_finalize(const ilqg_work *w, int max_iter, void *stream)
+{
+    k_finalize<<<nblk(w->B, 256), 256, 0, (cudaStream_t)stream>>>(*w, max_iter);
+    return check(cudaGetLastError(), "k_finalize");
+}
+
+int ilqgk_launch_count_active(const ilqg_work *w, int *d_counter, void *stream)
+{
+    if (check(cudaMemsetAsync(d_counter, 0, sizeof(int), (cudaStream_t)stream), "memset")) return -1;
+    k_count_active<<<nblk(w->B, 256), 256, 0, (cudaStream_t)stream>>>(*w, d_counter);
+    return check(cudaGetLastError(), "k_count_active");
+}
+
+int ilqgk_launch_scatter(const double *src, double *dst, int B, int Bp, int n_k, int n_i, void *stream)
+{
+    const size_t n = (size_t)B * n_k * n_i;
+    if (!n) return 0;
+    k_scatter<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, dst, B, Bp, n_k, n_i);
+    return check(cudaGetLastError(), "k_scatter");
+}
+
+int ilqgk_launch_gather(const double *src, const double *src_alt, const int *sel, double *dst, int B, int Bp, int n_k, int n_i, void *stream)
+{
+    const size_t n = (size_t)B * n_k * n_i;
+    if (!n) return 0;
+    k_gather<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, dst, sel, src_alt, B, Bp, n_k, n_i);
+    return check(cudaGetLastError(), "k_gather");
+}
+
+} /* extern "C" */

@@ -1,0 +1,53 @@
+/* ilqg_cuda.h -- C declarations of the thin CUDA layer (ilqg_cuda.cu) used by the C host code (ilqg_host.c).
+ * Plain pointers and sizes only; `stream` is a cudaStream_t passed as void*. All functions return 0 on success. */
+#ifndef ILQG_CUDA_H
+#define ILQG_CUDA_H
+#include <stddef.h>
+#include "ilqg_work.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ilqgk_dims_t {
+    int nx, nu, nqxx, nquu, nqxu, nv1, nv2, npf, nkp, n_mu_r, n_mu_f, n_mu_le, n_mu_fe, full_ddp, has_hx;
+} ilqgk_dims_t;
+
+const char *ilqgk_last_error(void);
+void ilqgk_dims(ilqgk_dims_t *d);
+const char *ilqgk_problem_name(void);
+int ilqgk_param_count(void);
+const char *ilqgk_param_name(int i);
+int ilqgk_param_size(int i);
+
+int ilqgk_device_count(void);
+int ilqgk_set_device(int dev);
+int ilqgk_malloc(void **p, size_t bytes);
+int ilqgk_free(void *p);
+int ilqgk_host_alloc(void **p, size_t bytes);
+int ilqgk_host_free(void *p);
+int ilqgk_memset(void *p, int v, size_t bytes, void *stream);
+int ilqgk_h2d(void *dst, const void *src, size_t bytes, void *stream);
+int ilqgk_d2h(void *dst, const void *src, size_t bytes, void *stream);
+int ilqgk_stream_create(void **s);
+int ilqgk_stream_destroy(void *s);
+int ilqgk_stream_sync(void *s);
+int ilqgk_event_create(void **e);
+int ilqgk_event_destroy(void *e);
+int ilqgk_event_record(void *e, void *s);
+int ilqgk_event_elapsed(void *a, void *b, float *ms);
+
+int ilqgk_launch_init(const ilqg_work *w, const ilqg_opts *o, const double *params, void *stream);
+int ilqgk_launch_derivs(const ilqg_work *w, const double *params, void *stream);
+int ilqgk_launch_backpass(const ilqg_work *w, const ilqg_opts *o, const double *params, int iter, void *stream);
+int ilqgk_launch_linesearch(const ilqg_work *w, const ilqg_opts *o, const double *params, int iter, void *stream);
+int ilqgk_launch_post(const ilqg_work *w, const ilqg_opts *o, const double *params, void *stream);
+int ilqgk_has_post(void);
+int ilqgk_launch_finalize(const ilqg_work *w, int max_iter, void *stream);
+int ilqgk_launch_count_active(const ilqg_work *w, int *d_counter, void *stream);
+int ilqgk_launch_scatter(const double *src, double *dst, int B, int Bp, int n_k, int n_i, void *stream);
+int ilqgk_launch_gather(const double *src, const double *src_alt, const int *sel, double *dst, int B, int Bp, int n_k, int n_i, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,609 @@
+/* ilqg_host.c -- C host side of the B200 batched iLQG solver (implements include/ilqg_b200.h).
+ *
+ * Plain C, no CUDA headers: device work goes through the thin layer declared in ilqg_cuda.h.  The solve loop of
+ * the reference (iLQG.c:239-363) becomes a fixed launch sequence per pass -- derivative kernel, backward-pass
+ * kernel, line-search kernel, (multiplier/cost kernel) -- over the whole batch; the per-problem control flow
+ * (lambda schedule, accept/reject, termination) lives in per-problem device state, so ragged convergence needs no
+ * host round trip per pass.  All problems that are still running are at the same pass index `iter`.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+
+#include "ilqg_b200.h"
+#include "ilqg_cuda.h"
+
+#define ACTIVE_CHECK_EVERY 8
+enum { TC_DERIVS = 0, TC_BACKPASS = 1, TC_LINESEARCH = 2, TC_POST = 3, TC_N = 4 };
+
+typedef struct {
+    void *start, *stop;
+    int cls;
+} ev_pair;
+
+struct ilqgb_handle {
+    int device, B, Bp, T, flags;
+    ilqgk_dims_t d;
+    ilqg_work w;
+    ilqg_opts o;
+    double *params;        /* flat, time-invariant */
+    void *stream;
+    int owns_stream;
+    int iter;              /* pass index of the running problems */
+    int started;
+    int trace_cap;         /* max_iter the trace arrays were sized for */
+    void **allocs;
+    int n_allocs, cap_allocs;
+    double *d_stage;       /* device staging for layout changes */
+    size_t stage_doubles;
+    int *d_counter;
+    int *h_counter;        /* pinned */
+    ev_pair *ev;
+    int n_ev, cap_ev, n_ev_created;
+    double t_ms[TC_N];
+    long t_n[TC_N];
+    char err[256];
+};
+
+static char g_create_err[256] = "";
+
+static int fail(ilqgb_handle *h, const char *msg)
+{
+    snprintf(h ? h->err : g_create_err, 256, "%s", msg);
+    return -1;
+}
+
+static int failk(ilqgb_handle *h) { return fail(h, ilqgk_last_error()); }
+
+static void *dalloc(ilqgb_handle *h, size_t bytes)
+{
+    void *p = NULL;
+    if (ilqgk_malloc(&p, bytes)) {
+        failk(h);
+        return NULL;
+    }
+    if (h->n_allocs == h->cap_allocs) {
+        h->cap_allocs = h->cap_allocs ? 2 * h->cap_allocs : 64;
+        h->allocs = (void **)realloc(h->allocs, sizeof(void *) * h->cap_allocs);
+    }
+    h->allocs[h->n_allocs++] = p;
+    return p;
+}
+
+/* ---- static facts -------------------------------------------------------------------------------------------------- */
+const char *ilqgb_problem_name(void) { return ilqgk_problem_name(); }
+int ilqgb_nx(void) { ilqgk_dims_t d; ilqgk_dims(&d); return d.nx; }
+int ilqgb_nu(void) { ilqgk_dims_t d; ilqgk_dims(&d); return d.nu; }
+int ilqgb_full_ddp(void) { ilqgk_dims_t d; ilqgk_dims(&d); return d.full_ddp; }
+int ilqgb_n_params(void) { return ilqgk_param_count(); }
+const char *ilqgb_param_name(int i) { return ilqgk_param_name(i); }
+int ilqgb_param_size(int i) { return ilqgk_param_size(i); }
+int ilqgb_device_count(void) { return ilqgk_device_count(); }
+int ilqgb_deriv_doubles_per_step(void) { ilqgk_dims_t d; ilqgk_dims(&d); return d.nv1 + (d.full_ddp ? d.nv2 : 0); }
+
+const char *ilqgb_last_error(const ilqgb_handle *h) { return h ? h->err : g_create_err; }
+
+/* ---- options (reference: standard_parameters iLQG.c:57-78, setOptParam iLQG.c:91-216) ----------------------------------- */
+static const double k_alpha_default[8] = {1.0, 0.3727594, 0.1389495, 0.0517947, 0.0193070, 0.0071969, 0.0026827, 0.0010000};
+
+void ilqgb_standard_parameters(ilqgb_handle *h)
+{
+    ilqg_opts *o = &h->o;
+    memset(o, 0, sizeof *o);
+    memcpy(o->alpha, k_alpha_default, sizeof k_alpha_default);
+    o->n_alpha = 8;
+    o->tolFun = 1e-7;
+    o->tolConstraint = 1e-7;
+    o->tolGrad = 1e-5;
+    o->max_iter = 20;
+    o->lambdaInit = 1;
+    o->dlambdaInit = 1;
+    o->lambdaFactor = 1.6;
+    o->lambdaMax = 1e10;
+    o->lambdaMin = 1e-6;
+    o->regType = 1;
+    o->zMin = 0.0;
+    o->w_pen_init_l = 1.0;
+    o->w_pen_init_f = 1.0;
+    o->w_pen_max_l = INFINITY;
+    o->w_pen_max_f = INFINITY;
+    o->w_pen_fact1 = 4.0;
+    o->w_pen_fact2 = 1.0;
+}
+
+typedef enum { V_POSITIVE, V_NONNEG, V_GE_ONE, V_ONE_TWO, V_ZERO_ONE, V_DEBUG } vrule;
+typedef struct {
+    const char *name;
+    size_t offset;
+    int is_int;
+    vrule rule;
+} opt_desc;
+
+#define OPT_D(field, rule) {#field, offsetof(ilqg_opts, field), 0, rule}
+#define OPT_I(field, rule) {#field, offsetof(ilqg_opts, field), 1, rule}
+static const opt_desc k_opts[] = {
+    OPT_D(tolFun, V_POSITIVE),      OPT_D(tolConstraint, V_POSITIVE), OPT_D(tolGrad, V_POSITIVE),
+    OPT_I(max_iter, V_NONNEG),      OPT_D(lambdaInit, V_NONNEG),      OPT_D(dlambdaInit, V_NONNEG),
+    OPT_D(lambdaFactor, V_GE_ONE),  OPT_D(lambdaMax, V_NONNEG),       OPT_D(lambdaMin, V_NONNEG),
+    OPT_I(regType, V_ONE_TWO),      OPT_D(zMin, V_ZERO_ONE),          OPT_D(w_pen_init_l, V_NONNEG),
+    OPT_D(w_pen_init_f, V_NONNEG),  OPT_D(w_pen_max_l, V_NONNEG),     OPT_D(w_pen_max_f, V_NONNEG),
+    OPT_D(w_pen_fact1, V_GE_ONE),   OPT_D(w_pen_fact2, V_GE_ONE),
+};
+
+static const char *rule_message(vrule r, double v)
+{
+    switch (r) {
+    case V_POSITIVE: return v <= 0.0 ? "parameter must be positive" : NULL;
+    case V_NONNEG: return v < 0.0 ? "parameter must be positive" : NULL;
+    case V_GE_ONE: return v < 1.0 ? "parameter must be > 1" : NULL;
+    case V_ONE_TWO: return (v < 1.0 || v > 2.0) ? "parameter must be in range [1..2]" : NULL;
+    case V_ZERO_ONE: return (v < 0.0 || v >= 1.0) ? "parameter must be in range [0..1)" : NULL;
+    case V_DEBUG: return (v < 0.0 || v > 6.0) ? "parameter must be in range [0..6]" : NULL;
+    }
+    return NULL;
+}
+
+const char *ilqgb_set_opt(ilqgb_handle *h, const char *name, const double *value, int n)
+{
+    size_t i;
+    if (strcmp(name, "alpha") == 0) {
+        int k;
+        for (k = 0; k < n; k++) {
+            if (value[k] < 0.0 || value[k] > 1.0) return "all alpha must be in the range [1.0..0.0)";
+            if (k > 0 && value[k] >= value[k - 1]) return "all alpha must be monotonically decreasing";
+        }
+        if (n > ILQG_MAX_ALPHA) return "at most 16 alpha values are supported";
+        memcpy(h->o.alpha, value, sizeof(double) * n);
+        h->o.n_alpha = n;
+        return NULL;
+    }
+    if (strcmp(name, "debug_level") == 0) { /* accepted and validated; the batched solver prints nothing */
+        if (n != 1) return "parameter must be scalar";
+        return rule_message(V_DEBUG, value[0]);
+    }
+    for (i = 0; i < sizeof k_opts / sizeof k_opts[0]; i++) {
+        const opt_desc *d = &k_opts[i];
+        const char *msg;
+        if (strcmp(name, d->name) != 0) continue;
+        if (n != 1) return "parameter must be scalar";
+        if ((msg = rule_message(d->rule, value[0])) != NULL) return msg;
+        if (d->is_int)
+            *(int *)((char *)&h->o + d->offset) = (int)value[0];
+        else
+            *(double *)((char *)&h->o + d->offset) = value[0];
+        return NULL;
+    }
+    return "no such parameter";
+}
+
+int ilqgb_set_param(ilqgb_handle *h, int index, const double *value, int n)
+{
+    int i, off = 0;
+    if (index < 0 || index >= ilqgk_param_count()) return fail(h, "parameter index out of range");
+    if (ilqgk_param_size(index) == -1) return fail(h, "[k]-indexed parameters are not supported by this build");
+    if (n != ilqgk_param_size(index)) return fail(h, "wrong parameter length");
+    for (i = 0; i < index; i++)
+        if (ilqgk_param_size(i) > 0) off += ilqgk_param_size(i);
+    memcpy(h->params + off, value, sizeof(double) * n);
+    return 0;
+}
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------------------------- */
+#define DALLOC(dst, type, count)                                   \
+    do {                                                           \
+        (dst) = (type *)dalloc(h, sizeof(type) * (size_t)(count)); \
+        if (!(dst)) goto oom;                                      \
+    } while (0)
+
+ilqgb_handle *ilqgb_create(int device, int batch, int n_hor, int flags, void *stream)
+{
+    ilqgb_handle *h;
+    size_t Bp, T = (size_t)n_hor;
+    if (batch < 1 || n_hor < 1) {
+        fail(NULL, "batch and n_hor must be >= 1");
+        return NULL;
+    }
+    if (ilqgk_device_count() < 1) {
+        fail(NULL, "no CUDA device available: this library has no CPU fallback");
+        return NULL;
+    }
+    if (ilqgk_set_device(device)) {
+        failk(NULL);
+        return NULL;
+    }
+    h = (ilqgb_handle *)calloc(1, sizeof *h);
+    h->device = device;
+    h->B = batch;
+    h->Bp = (batch + 31) / 32 * 32;
+    h->T = n_hor;
+    h->flags = flags;
+    ilqgk_dims(&h->d);
+    if (h->d.nkp > 0) {
+        fail(NULL, "[k]-indexed parameters are not supported by this build");
+        free(h);
+        return NULL;
+    }
+    h->params = (double *)calloc((size_t)(h->d.npf > 0 ? h->d.npf : 1), sizeof(double));
+    ilqgb_standard_parameters(h);
+    if (stream) {
+        h->stream = stream;
+    } else {
+        if (ilqgk_stream_create(&h->stream)) goto oom;
+        h->owns_stream = 1;
+    }
+    Bp = (size_t)h->Bp;
+    {
+        const ilqgk_dims_t *d = &h->d;
+        ilqg_work *w = &h->w;
+        int i;
+        w->B = batch;
+        w->Bp = h->Bp;
+        w->T = n_hor;
+        for (i = 0; i < 2; i++) {
+            DALLOC(w->X[i], double, (T + 1) * d->nx * Bp);
+            DALLOC(w->U[i], double, T * d->nu * Bp);
+        }
+        DALLOC(w->x0, double, d->nx * Bp);
+        DALLOC(w->l, double, T * d->nu * Bp);
+        DALLOC(w->Lg, double, T * d->nu * d->nx * Bp);
+        DALLOC(w->V1, double, T * d->nv1 * Bp);
+        DALLOC(w->V2, double, d->full_ddp ? T * d->nv2 * Bp : 1);
+        DALLOC(w->FD, double, (d->nx + d->nqxx) * Bp);
+        DALLOC(w->muR, double, T * (d->n_mu_r ? d->n_mu_r : 0) * Bp + 1);
+        DALLOC(w->lastR, double, T * (d->n_mu_r ? d->n_mu_r : 0) * Bp + 1);
+        DALLOC(w->muF, double, d->n_mu_f * Bp + 1);
+        DALLOC(w->lastF, double, d->n_mu_f * Bp + 1);
+        w->pk = NULL;
+        DALLOC(w->cost, double, Bp);
+        DALLOC(w->new_cost, double, Bp);
+        DALLOC(w->dcost, double, Bp);
+        DALLOC(w->expected, double, Bp);
+        DALLOC(w->lambda, double, Bp);
+        DALLOC(w->dlambda, double, Bp);
+        DALLOC(w->g_norm, double, Bp);
+        DALLOC(w->dV0, double, Bp);
+        DALLOC(w->dV1, double, Bp);
+        DALLOC(w->w_pen_l, double, Bp);
+        DALLOC(w->w_pen_f, double, Bp);
+        DALLOC(w->cur, int, Bp);
+        DALLOC(w->status, int, Bp);
+        DALLOC(w->new_deriv, int, Bp);
+        DALLOC(w->deriv_fail, int, Bp);
+        DALLOC(w->iterations, int, Bp);
+        DALLOC(w->result, int, Bp);
+        DALLOC(w->n_ls, int, Bp);
+        DALLOC(w->n_bp, int, Bp);
+        DALLOC(w->bp_done, int, Bp);
+        DALLOC(w->post_mode, int, Bp);
+        ilqgk_memset(w->status, 0, sizeof(int) * Bp, h->stream);
+        ilqgk_memset(w->cur, 0, sizeof(int) * Bp, h->stream);
+        if (flags & ILQGB_TRACE) {
+            DALLOC(w->tr_clamp, int, T * Bp);
+            ilqgk_memset(w->tr_clamp, 0, sizeof(int) * T * Bp, h->stream);
+        }
+        DALLOC(h->d_counter, int, 1);
+    }
+    if (ilqgk_host_alloc((void **)&h->h_counter, sizeof(int))) goto oom;
+    return h;
+oom:
+    snprintf(g_create_err, sizeof g_create_err, "%s", h->err[0] ? h->err : ilqgk_last_error());
+    ilqgb_destroy(h);
+    return NULL;
+}
+
+void ilqgb_destroy(ilqgb_handle *h)
+{
+    int i;
+    if (!h) return;
+    ilqgk_set_device(h->device);
+    if (h->stream) ilqgk_stream_sync(h->stream);
+    for (i = 0; i < h->n_allocs; i++) ilqgk_free(h->allocs[i]);
+    free(h->allocs);
+    for (i = 0; i < h->n_ev_created; i++) {
+        ilqgk_event_destroy(h->ev[i].start);
+        ilqgk_event_destroy(h->ev[i].stop);
+    }
+    free(h->ev);
+    if (h->h_counter) ilqgk_host_free(h->h_counter);
+    if (h->owns_stream && h->stream) ilqgk_stream_destroy(h->stream);
+    free(h->params);
+    free(h);
+}
+
+static int ensure_stage(ilqgb_handle *h, size_t doubles)
+{
+    if (doubles <= h->stage_doubles) return 0;
+    /* the old staging buffer stays in the allocation list and is freed with the handle */
+    h->d_stage = (double *)dalloc(h, sizeof(double) * doubles);
+    if (!h->d_stage) {
+        h->stage_doubles = 0;
+        return -1;
+    }
+    h->stage_doubles = doubles;
+    return 0;
+}
+
+static int ensure_traces(ilqgb_handle *h)
+{
+    size_t n;
+    if (!(h->flags & ILQGB_TRACE) || h->o.max_iter <= h->trace_cap) return 0;
+    n = (size_t)h->o.max_iter * h->Bp;
+    h->w.tr_lambda = (double *)dalloc(h, sizeof(double) * n);
+    h->w.tr_newcost = (double *)dalloc(h, sizeof(double) * n);
+    h->w.tr_alpha = (int *)dalloc(h, sizeof(int) * n);
+    if (!h->w.tr_lambda || !h->w.tr_newcost || !h->w.tr_alpha) return -1;
+    h->trace_cap = h->o.max_iter;
+    return 0;
+}
+
+/* ---- data movement ------------------------------------------------------------------------------------------------------------ */
+int ilqgb_upload(ilqgb_handle *h, const double *x0, const double *u_nom)
+{
+    const size_t B = (size_t)h->B, T = (size_t)h->T, nx = (size_t)h->d.nx, nu = (size_t)h->d.nu;
+    if (ilqgk_set_device(h->device)) return failk(h);
+    if (ensure_stage(h, B * T * nu + B * nx)) return -1;
+    if (ilqgk_h2d(h->d_stage, u_nom, sizeof(double) * B * T * nu, h->stream)) return failk(h);
+    if (ilqgk_h2d(h->d_stage + B * T * nu, x0, sizeof(double) * B * nx, h->stream)) return failk(h);
+    if (ilqgk_launch_scatter(h->d_stage, h->w.U[0], h->B, h->Bp, h->T, h->d.nu, h->stream)) return failk(h);
+    if (ilqgk_launch_scatter(h->d_stage + B * T * nu, h->w.x0, h->B, h->Bp, 1, h->d.nx, h->stream)) return failk(h);
+    h->started = 0;
+    return 0;
+}
+
+static int gather_to_host(ilqgb_handle *h, const double *src, const double *alt, const int *sel, int n_k, int n_i, double *out)
+{
+    const size_t n = (size_t)h->B * n_k * n_i;
+    if (!n) return 0;
+    if (ensure_stage(h, n)) return -1;
+    if (ilqgk_launch_gather(src, alt, sel, h->d_stage, h->B, h->Bp, n_k, n_i, h->stream)) return failk(h);
+    if (ilqgk_d2h(out, h->d_stage, sizeof(double) * n, h->stream)) return failk(h);
+    return 0;
+}
+
+int ilqgb_download(ilqgb_handle *h, double *x, double *u, double *cost, int *iterations, int *result, int *n_linesearch)
+{
+    const size_t B = (size_t)h->B;
+    if (ilqgk_set_device(h->device)) return failk(h);
+    /* the staging buffer is reused: serialise x and u through the stream (stream order keeps this correct) */
+    if (x) {
+        if (gather_to_host(h, h->w.X[0], h->w.X[1], h->w.cur, h->T + 1, h->d.nx, x)) return -1;
+        if (ilqgk_stream_sync(h->stream)) return failk(h);
+    }
+    if (u) {
+        if (gather_to_host(h, h->w.U[0], h->w.U[1], h->w.cur, h->T, h->d.nu, u)) return -1;
+        if (ilqgk_stream_sync(h->stream)) return failk(h);
+    }
+    if (cost && ilqgk_d2h(cost, h->w.cost, sizeof(double) * B, h->stream)) return failk(h);
+    if (iterations && ilqgk_d2h(iterations, h->w.iterations, sizeof(int) * B, h->stream)) return failk(h);
+    if (result && ilqgk_d2h(result, h->w.result, sizeof(int) * B, h->stream)) return failk(h);
+    if (n_linesearch && ilqgk_d2h(n_linesearch, h->w.n_ls, sizeof(int) * B, h->stream)) return failk(h);
+    if (ilqgk_stream_sync(h->stream)) return failk(h);
+    return 0;
+}
+
+/* ---- timing -------------------------------------------------------------------------------------------------------------------- */
+static ev_pair *timing_begin(ilqgb_handle *h, int cls)
+{
+    ev_pair *p;
+    if (!(h->flags & ILQGB_TIMING)) return NULL;
+    if (h->n_ev == h->cap_ev) {
+        h->cap_ev = h->cap_ev ? 2 * h->cap_ev : 256;
+        h->ev = (ev_pair *)realloc(h->ev, sizeof(ev_pair) * h->cap_ev);
+    }
+    p = &h->ev[h->n_ev];
+    if (h->n_ev == h->n_ev_created) {
+        if (ilqgk_event_create(&p->start) || ilqgk_event_create(&p->stop)) return NULL;
+        h->n_ev_created++;
+    }
+    h->n_ev++;
+    p->cls = cls;
+    ilqgk_event_record(p->start, h->stream);
+    return p;
+}
+
+static void timing_end(ilqgb_handle *h, ev_pair *p)
+{
+    if (p) ilqgk_event_record(p->stop, h->stream);
+}
+
+int ilqgb_timing(ilqgb_handle *h, double *ms, long *launches, int reset)
+{
+    int i;
+    if (ilqgk_set_device(h->device)) return failk(h);
+    if (ilqgk_stream_sync(h->stream)) return failk(h);
+    for (i = 0; i < h->n_ev; i++) {
+        float t = 0.f;
+        if (ilqgk_event_elapsed(h->ev[i].start, h->ev[i].stop, &t) == 0) {
+            h->t_ms[h->ev[i].cls] += t;
+            h->t_n[h->ev[i].cls] += 1;
+        }
+    }
+    h->n_ev = 0;
+    for (i = 0; i < TC_N; i++) {
+        if (ms) ms[i] = h->t_ms[i];
+        if (launches) launches[i] = h->t_n[i];
+        if (reset) {
+            h->t_ms[i] = 0.0;
+            h->t_n[i] = 0;
+        }
+    }
+    return 0;
+}
+
+/* ---- the solve ------------------------------------------------------------------------------------------------------------------ */
+int ilqgb_start(ilqgb_handle *h)
+{
+    if (ilqgk_set_device(h->device)) return failk(h);
+    if (ensure_traces(h)) return -1;
+    if (ilqgk_launch_init(&h->w, &h->o, h->params, h->stream)) return failk(h);
+    h->iter = 0;
+    h->started = 1;
+    return 0;
+}
+
+static int launch_pass(ilqgb_handle *h, int do_derivs, int do_back, int do_ls)
+{
+    ev_pair *p;
+    if (do_derivs) {
+        p = timing_begin(h, TC_DERIVS);
+        if (ilqgk_launch_derivs(&h->w, h->params, h->stream)) return failk(h);
+        timing_end(h, p);
+    }
+    if (do_back) {
+        p = timing_begin(h, TC_BACKPASS);
+        if (ilqgk_launch_backpass(&h->w, &h->o, h->params, h->iter, h->stream)) return failk(h);
+        timing_end(h, p);
+    }
+    if (do_ls) {
+        p = timing_begin(h, TC_LINESEARCH);
+        if (ilqgk_launch_linesearch(&h->w, &h->o, h->params, h->iter, h->stream)) return failk(h);
+        timing_end(h, p);
+        if (ilqgk_has_post()) {
+            p = timing_begin(h, TC_POST);
+            if (ilqgk_launch_post(&h->w, &h->o, h->params, h->stream)) return failk(h);
+            timing_end(h, p);
+        }
+    }
+    return 0;
+}
+
+int ilqgb_active(ilqgb_handle *h)
+{
+    if (ilqgk_set_device(h->device)) return failk(h);
+    if (ilqgk_launch_count_active(&h->w, h->d_counter, h->stream)) return failk(h);
+    if (ilqgk_d2h(h->h_counter, h->d_counter, sizeof(int), h->stream)) return failk(h);
+    if (ilqgk_stream_sync(h->stream)) return failk(h);
+    return *h->h_counter;
+}
+
+int ilqgb_iterate(ilqgb_handle *h, int n_passes)
+{
+    int done = 0;
+    if (!h->started) return fail(h, "ilqgb_start has not been called");
+    if (ilqgk_set_device(h->device)) return failk(h);
+    while (done < n_passes && h->iter < h->o.max_iter) {
+        if (launch_pass(h, 1, 1, 1)) return -1;
+        h->iter++;
+        done++;
+        if (h->iter % ACTIVE_CHECK_EVERY == 0 && h->iter < h->o.max_iter) {
+            const int a = ilqgb_active(h);
+            if (a < 0) return -1;
+            if (a == 0) break;
+        }
+    }
+    return done;
+}
+
+int ilqgb_finish(ilqgb_handle *h)
+{
+    if (ilqgk_set_device(h->device)) return failk(h);
+    /* problems that are still running after max_iter passes: iLQG.c:365-377 */
+    if (h->iter >= h->o.max_iter && ilqgk_launch_finalize(&h->w, h->o.max_iter, h->stream)) return failk(h);
+    return 0;
+}
+
+int ilqgb_solve(ilqgb_handle *h)
+{
+    if (ilqgb_start(h)) return -1;
+    while (h->iter < h->o.max_iter) {
+        const int n = ilqgb_iterate(h, h->o.max_iter - h->iter);
+        if (n < 0) return -1;
+        if (h->iter < h->o.max_iter) { /* stopped early: everything converged */
+            if (ilqgb_active(h) == 0) break;
+        }
+    }
+    /* when the loop ran out of passes, or max_iter == 0, mark the stragglers */
+    if (ilqgk_launch_finalize(&h->w, h->o.max_iter, h->stream)) return failk(h);
+    return 0;
+}
+
+int ilqgb_sync(ilqgb_handle *h)
+{
+    if (ilqgk_set_device(h->device)) return failk(h);
+    return ilqgk_stream_sync(h->stream) ? failk(h) : 0;
+}
+
+int ilqgb_phase_derivs(ilqgb_handle *h) { return ilqgk_set_device(h->device) ? failk(h) : launch_pass(h, 1, 0, 0); }
+int ilqgb_phase_backpass(ilqgb_handle *h) { return ilqgk_set_device(h->device) ? failk(h) : launch_pass(h, 0, 1, 0); }
+int ilqgb_phase_linesearch(ilqgb_handle *h) { return ilqgk_set_device(h->device) ? failk(h) : launch_pass(h, 0, 0, 1); }
+
+/* ---- read-back -------------------------------------------------------------------------------------------------------------------- */
+long ilqgb_get(ilqgb_handle *h, const char *f, double *out)
+{
+    const ilqg_work *w = &h->w;
+    const ilqgk_dims_t *d = &h->d;
+    const size_t B = (size_t)h->B;
+    const double *scal = NULL;
+    if (ilqgk_set_device(h->device)) return failk(h);
+    if (!strcmp(f, "cost")) scal = w->cost;
+    else if (!strcmp(f, "new_cost")) scal = w->new_cost;
+    else if (!strcmp(f, "dcost")) scal = w->dcost;
+    else if (!strcmp(f, "expected")) scal = w->expected;
+    else if (!strcmp(f, "lambda")) scal = w->lambda;
+    else if (!strcmp(f, "dlambda")) scal = w->dlambda;
+    else if (!strcmp(f, "g_norm")) scal = w->g_norm;
+    else if (!strcmp(f, "dV0")) scal = w->dV0;
+    else if (!strcmp(f, "dV1")) scal = w->dV1;
+    else if (!strcmp(f, "w_pen_l")) scal = w->w_pen_l;
+    else if (!strcmp(f, "w_pen_f")) scal = w->w_pen_f;
+    if (scal) {
+        if (ilqgk_d2h(out, scal, sizeof(double) * B, h->stream) || ilqgk_stream_sync(h->stream)) return failk(h);
+        return (long)B;
+    }
+    {
+        const double *src = NULL, *alt = NULL;
+        const int *sel = NULL;
+        int n_k = 0, n_i = 0;
+        if (!strcmp(f, "x")) { src = w->X[0]; alt = w->X[1]; sel = w->cur; n_k = h->T + 1; n_i = d->nx; }
+        else if (!strcmp(f, "u")) { src = w->U[0]; alt = w->U[1]; sel = w->cur; n_k = h->T; n_i = d->nu; }
+        else if (!strcmp(f, "l")) { src = w->l; n_k = h->T; n_i = d->nu; }
+        else if (!strcmp(f, "L")) { src = w->Lg; n_k = h->T; n_i = d->nu * d->nx; }
+        else if (!strcmp(f, "v1")) { src = w->V1; n_k = h->T; n_i = d->nv1; }
+        else if (!strcmp(f, "v2") && d->full_ddp) { src = w->V2; n_k = h->T; n_i = d->nv2; }
+        else if (!strcmp(f, "fd")) { src = w->FD; n_k = 1; n_i = d->nx + d->nqxx; }
+        else if (!strcmp(f, "mu_f")) { src = w->muF; n_k = 1; n_i = d->n_mu_f; }
+        else if (!strcmp(f, "mu_r")) { src = w->muR; n_k = h->T; n_i = d->n_mu_r; }
+        else if (!strcmp(f, "tr_lambda") && w->tr_lambda) { src = w->tr_lambda; n_k = h->trace_cap; n_i = 1; }
+        else if (!strcmp(f, "tr_newcost") && w->tr_newcost) { src = w->tr_newcost; n_k = h->trace_cap; n_i = 1; }
+        else return fail(h, "unknown field");
+        if (gather_to_host(h, src, alt, sel, n_k, n_i, out)) return -1;
+        if (ilqgk_stream_sync(h->stream)) return failk(h);
+        return (long)(B * n_k * n_i);
+    }
+}
+
+long ilqgb_get_int(ilqgb_handle *h, const char *f, int *out)
+{
+    const ilqg_work *w = &h->w;
+    const size_t B = (size_t)h->B, Bp = (size_t)h->Bp;
+    const int *scal = NULL, *arr = NULL;
+    size_t n_k = 0;
+    if (ilqgk_set_device(h->device)) return failk(h);
+    if (!strcmp(f, "iterations")) scal = w->iterations;
+    else if (!strcmp(f, "result")) scal = w->result;
+    else if (!strcmp(f, "status")) scal = w->status;
+    else if (!strcmp(f, "n_linesearch")) scal = w->n_ls;
+    else if (!strcmp(f, "n_backpass")) scal = w->n_bp;
+    else if (!strcmp(f, "cur")) scal = w->cur;
+    if (scal) {
+        if (ilqgk_d2h(out, scal, sizeof(int) * B, h->stream) || ilqgk_stream_sync(h->stream)) return failk(h);
+        return (long)B;
+    }
+    if (!strcmp(f, "tr_alpha") && w->tr_alpha) { arr = w->tr_alpha; n_k = (size_t)h->trace_cap; }
+    else if (!strcmp(f, "tr_clamp") && w->tr_clamp) { arr = w->tr_clamp; n_k = (size_t)h->T; }
+    else return fail(h, "unknown field");
+    {
+        /* small, test-only path: copy [n_k][Bp] and transpose on the host */
+        int *tmp = (int *)malloc(sizeof(int) * n_k * Bp);
+        size_t b, k;
+        if (ilqgk_d2h(tmp, arr, sizeof(int) * n_k * Bp, h->stream) || ilqgk_stream_sync(h->stream)) {
+            free(tmp);
+            return failk(h);
+        }
+        for (b = 0; b < B; b++)
+            for (k = 0; k < n_k; k++) out[b * n_k + k] = tmp[k * Bp + b];
+        free(tmp);
+        return (long)(B * n_k);
+    }
+}

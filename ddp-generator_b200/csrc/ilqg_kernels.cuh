@@ -1,0 +1,963 @@
+/* ilqg_kernels.cuh -- batched iLQG / control-limited DDP kernels for sm_100a (B200), templated on a generated
+ * problem struct P (problems/<name>/<name>_device.cuh).
+ *
+ * Execution model ("lane per problem"): the batch of independent problems is the parallel axis.  Lane b of a warp
+ * owns problem b for the phases that are sequential in time (backward pass, rollouts) and keeps its value
+ * function, Q-function and box-QP state in registers; the derivative pass is parallel over (problem, timestep).
+ * Every array in HBM is structure-of-arrays with the problem index fastest ([k][field][b]), so each warp-level load
+ * or store touches one fully used 256-byte segment.
+ *
+ * Bit-exact parity with the reference C solver is a design constraint: every floating-point operation is issued
+ * in the reference's order (single accumulators, ascending indices, explicit symmetrisation; see the citations on
+ * each function), the translation unit is compiled with -fmad=false, and transcendental functions come from
+ * dm_math.h on both sides.
+ *
+ * Reference functions restated here (file:line in /root/reference):
+ *   add_mul_vec / add_square_tri / add_mul2_tri   matMult.c:3-12 / 14-46 / 48-72
+ *   box_qp (+ masked Cholesky / inverse)          boxQP.c:39-238, cholesky.c:6-27, 51-74
+ *   k_backpass                                    back_pass.c:38-257 + iLQG.c:261-303 (lambda loop, gradient exit)
+ *   k_rollout                                     iLQG_func.tem:121-185 (forward_pass), line_search.c:33-78,
+ *                                                 iLQG.c:311-361 (accept / reject), iLQG_mex.c:108-120 (initial)
+ *   k_derivs                                      iLQG_func.tem:187-221 (calc_derivs)
+ *   k_post                                        iLQG_func.tem:417-509 (update_multipliers) + cost-only pass
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "dm_math.h"
+#include "ilqg_work.h"
+
+namespace ilqg {
+
+constexpr int MAX_ALPHA = ILQG_MAX_ALPHA;
+constexpr int BP_BLOCK = 64;   /* threads per block for the sequential-in-time kernels */
+constexpr int DV_BLOCK = 128;  /* threads per block for the derivative kernel */
+
+enum { ST_RUNNING = 0, ST_DONE = 1 };
+enum { POST_NONE = 0, POST_MULT = 1, POST_COST = 2 };
+
+using Opts = ilqg_opts;
+using Work = ilqg_work;
+
+template <class P> struct ParamBlock { double v[P::NPF]; };
+
+__device__ __forceinline__ double dmax(double a, double b) { return (a > b) ? a : b; }
+__device__ __forceinline__ double dmin(double a, double b) { return (a < b) ? a : b; }
+__host__ __device__ constexpr int utri(int r, int c) { return (c * (c + 1)) / 2 + r; }
+__host__ __device__ constexpr int symtri(int r, int c) { return r > c ? utri(c, r) : utri(r, c); }
+
+/* ---- small dense algebra, operation order of matMult.c ---------------------------------------------------------- */
+template <int NR, int NC>
+__device__ __forceinline__ void add_mul_vec(double *base, const double *a, const double *b)
+{
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+#pragma unroll
+        for (int r = 0; r < NR; r++)
+            base[c] += a[r] * b[r + c * NR];
+}
+
+template <int NR, int NC>
+__device__ __forceinline__ void add_square_tri(double *base, const double *B, const double *a)
+{
+    double ba[NR * NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int s = 0; s < NR; s++)
+                acc += B[symtri(r, s)] * a[s + c * NR];
+            ba[r + c * NR] = acc;
+        }
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+#pragma unroll
+        for (int r = 0; r <= c; r++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int s = 0; s < NR; s++)
+                acc += a[s + r * NR] * ba[s + c * NR];
+            if (r != c) {
+#pragma unroll
+                for (int s = 0; s < NR; s++)
+                    acc += a[s + c * NR] * ba[s + r * NR];
+                acc *= 0.5;
+            }
+            base[utri(r, c)] += acc;
+        }
+}
+
+template <int NRA, int NCA, int NCC>
+__device__ __forceinline__ void add_mul2_tri(double *base, const double *B, const double *a, const double *c)
+{
+    double bc[NRA * NCC];
+#pragma unroll
+    for (int j = 0; j < NCC; j++)
+#pragma unroll
+        for (int r = 0; r < NRA; r++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int s = 0; s < NRA; s++)
+                acc += B[symtri(r, s)] * c[s + j * NRA];
+            bc[r + j * NRA] = acc;
+        }
+#pragma unroll
+    for (int i = 0; i < NCA; i++)
+#pragma unroll
+        for (int j = 0; j < NCC; j++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int s = 0; s < NRA; s++)
+                acc += a[s + i * NRA] * bc[s + j * NRA];
+            base[i + j * NCA] += acc;
+        }
+}
+
+/* ---- projected-Newton box QP ------------------------------------------------------------------------------------------
+ * The reference compacts the free rows/columns before factorising (boxQP.c:129-146).  Here the factor U and the
+ * inverse live in FULL index space and clamped indices are skipped by predicate: the same multiplications and
+ * additions happen in the same order, but every array index is a compile-time constant, so all QP state stays in
+ * registers. */
+template <int M>
+__device__ __forceinline__ double qp_value(const double *H, const double *g, const double *x)
+{
+    double val = 0.0;
+#pragma unroll
+    for (int i = 0; i < M; i++) {
+        double hx = 0.0;
+#pragma unroll
+        for (int j = 0; j < M; j++)
+            hx += H[symtri(i, j)] * x[j];
+        val += x[i] * (g[i] + 0.5 * hx);
+    }
+    return val;
+}
+
+template <int M>
+__device__ __forceinline__ int box_qp(const double *H, const double *g, const double *lower, const double *upper,
+                                      double *x, int *clamped, double *invH, int &n_free_out)
+{
+    constexpr int MP = (M * (M + 1)) / 2;
+    const double min_grad = 1e-8, min_rel_improve = 1e-8, step_dec = 0.6, min_step = 1e-22, armijo = 0.1;
+    double U[MP], grad[M], gc[M], search[M], w[M];
+    double value, oldvalue = 0.0;
+
+#pragma unroll
+    for (int i = 0; i < M; i++) {
+        if (x[i] > upper[i]) x[i] = upper[i];
+        if (x[i] < lower[i]) x[i] = lower[i];
+        clamped[i] = 0;
+    }
+    value = qp_value<M>(H, g, x);
+
+    for (int iter = 0; iter < 100; iter++) {
+        if (iter > 0 && (oldvalue - value) < min_rel_improve * fabs(oldvalue))
+            return 4;
+        oldvalue = value;
+
+        int n_free = 0;
+        bool changed = false, all_clamped = true;
+        double gsq = 0.0;
+#pragma unroll
+        for (int i = 0; i < M; i++) {
+            double hx = 0.0;
+#pragma unroll
+            for (int j = 0; j < M; j++)
+                hx += H[symtri(i, j)] * x[j];
+            grad[i] = g[i] + hx;
+            const int was = clamped[i];
+            if (x[i] <= lower[i] && grad[i] > 0)
+                clamped[i] = 1;
+            else if (x[i] >= upper[i] && grad[i] < 0)
+                clamped[i] = 2;
+            else {
+                clamped[i] = 0;
+                all_clamped = false;
+                gsq += grad[i] * grad[i];
+                n_free++;
+            }
+            if ((!was) != (!clamped[i]))
+                changed = true;
+        }
+        n_free_out = n_free;
+        if (all_clamped)
+            return 6;
+
+        if (iter == 0 || changed) {
+            /* U'U = H(free,free)  (cholesky.c:6-27) */
+            bool pd = true;
+#pragma unroll
+            for (int col = 0; col < M; col++) {
+#pragma unroll
+                for (int row = 0; row <= col; row++) {
+                    if (clamped[col] || clamped[row] || !pd) continue;
+                    double dot = 0;
+#pragma unroll
+                    for (int k = 0; k < row; k++)
+                        if (!clamped[k])
+                            dot += U[utri(k, col)] * U[utri(k, row)];
+                    const double rem = H[utri(row, col)] - dot;
+                    if (row == col) {
+                        if (rem <= 0.0)
+                            pd = false;
+                        else
+                            U[utri(row, col)] = sqrt(rem);
+                    } else {
+                        U[utri(row, col)] = 1.0 / U[utri(row, row)] * rem;
+                    }
+                }
+            }
+            if (!pd)
+                return -1;
+            /* explicit inverse, one unit right-hand side per free column (cholesky.c:51-74) */
+#pragma unroll
+            for (int col = 0; col < M; col++) {
+                if (clamped[col]) continue;
+                w[col] = 1.0;
+#pragma unroll
+                for (int k = col + 1; k < M; k++)
+                    w[k] = 0.0;
+#pragma unroll
+                for (int k = col; k < M; k++) {
+                    if (clamped[k]) continue;
+#pragma unroll
+                    for (int i = col; i < k; i++)
+                        if (!clamped[i])
+                            w[k] -= w[i] * U[utri(i, k)];
+                    w[k] /= U[utri(k, k)];
+                }
+#pragma unroll
+                for (int k = M - 1; k >= col; k--) {
+                    if (clamped[k]) continue;
+#pragma unroll
+                    for (int i = k + 1; i < M; i++)
+                        if (!clamped[i])
+                            w[k] -= w[i] * U[utri(k, i)];
+                    w[k] /= U[utri(k, k)];
+                    invH[utri(col, k)] = w[k];
+                }
+            }
+        }
+        if (gsq < min_grad * min_grad)
+            return 5;
+
+        /* search = -Hfree^-1 (g + H x_clamped) - x on the free set (boxQP.c:153-177) */
+#pragma unroll
+        for (int i = 0; i < M; i++) {
+            if (clamped[i]) continue;
+            double hc = 0.0;
+#pragma unroll
+            for (int j = 0; j < M; j++)
+                if (clamped[j])
+                    hc += H[symtri(i, j)] * x[j];
+            gc[i] = g[i] + hc;
+        }
+#pragma unroll
+        for (int i = 0; i < M; i++) {
+            if (clamped[i]) {
+                search[i] = 0.0;
+                continue;
+            }
+            double s = -x[i];
+#pragma unroll
+            for (int j = 0; j < M; j++)
+                if (!clamped[j])
+                    s -= invH[symtri(i, j)] * gc[j];
+            search[i] = s;
+        }
+        double sdotg = 0.0;
+#pragma unroll
+        for (int i = 0; i < M; i++)
+            sdotg += search[i] * grad[i];
+        if (sdotg >= 0.0)
+            return -2;
+
+        /* Armijo backtracking along the projected step (boxQP.c:198-227) */
+        double step = 1.0, vc;
+        double xc[M];
+        for (;;) {
+#pragma unroll
+            for (int i = 0; i < M; i++) {
+                xc[i] = x[i] + step * search[i];
+                if (xc[i] > upper[i]) xc[i] = upper[i];
+                if (xc[i] < lower[i]) xc[i] = lower[i];
+            }
+            vc = qp_value<M>(H, g, xc);
+            if (((vc - oldvalue) / (step * sdotg)) >= armijo)
+                break;
+            step = step * step_dec;
+            if (step < min_step)
+                return 2;
+        }
+#pragma unroll
+        for (int i = 0; i < M; i++)
+            x[i] = xc[i];
+        value = vc;
+    }
+    return 1;
+}
+
+/* ---- per-step dense record the backward pass works on ------------------------------------------------------------- */
+template <class P> struct Dense {
+    double fx[P::NX * P::NX], fu[P::NX * P::NU], cx[P::NX], cxx[P::NQXX], cu[P::NU], cuu[P::NQUU], cxu[P::NQXU];
+    double lower[P::NU], upper[P::NU];
+    double lower_sign[P::NU], upper_sign[P::NU], lower_hx[P::NX * P::NU], upper_hx[P::NX * P::NU];
+};
+
+__device__ __forceinline__ void finish(const Work &w, int b, int iter, int result)
+{
+    w.status[b] = ST_DONE;
+    w.iterations[b] = iter;
+    w.result[b] = result;
+}
+
+__device__ __forceinline__ void raise_lambda(const Opts &o, double &lambda, double &dlambda)
+{
+    dlambda = dmax(dlambda * o.lambdaFactor, o.lambdaFactor);   /* iLQG.c:272-273, 342-343 */
+    lambda = dmax(lambda * dlambda, o.lambdaMin);
+}
+
+__device__ __forceinline__ void lower_lambda(const Opts &o, double &lambda, double &dlambda)
+{
+    dlambda = dmin(dlambda / o.lambdaFactor, 1.0 / o.lambdaFactor);   /* iLQG.c:298-299, 317-318 */
+    lambda = lambda * dlambda * (double)(lambda > o.lambdaMin);
+}
+
+/* =====================================================================================================================
+ * K1: derivative pass, one thread per (problem, timestep); k == T evaluates the final-cost derivatives.
+ * ===================================================================================================================== */
+template <class P, bool FULL>
+__global__ void __launch_bounds__(DV_BLOCK) k_derivs(Work w, ParamBlock<P> pb)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (b >= w.B) return;
+    if (w.status[b] != ST_RUNNING || !w.new_deriv[b]) return;
+    const size_t Bp = w.Bp;
+    const int cur = w.cur[b];
+    double x[P::NX], u[P::NU], mu[P::N_MU_R + P::N_MU_F + 1];
+    const double *Xc = w.X[cur] + (size_t)k * P::NX * Bp + b;
+#pragma unroll
+    for (int i = 0; i < P::NX; i++) x[i] = Xc[i * Bp];
+    bool ok;
+    if (k < w.T) {
+        const double *Uc = w.U[cur] + (size_t)k * P::NU * Bp + b;
+#pragma unroll
+        for (int i = 0; i < P::NU; i++) u[i] = Uc[i * Bp];
+#pragma unroll
+        for (int i = 0; i < P::N_MU_R; i++) mu[i] = w.muR[((size_t)k * P::N_MU_R + i) * Bp + b];
+        double v1[P::NV1], v2[P::NV2];
+        const double w_pen = w.w_pen_l[b];
+        if (FULL)
+            ok = P::derivs_full(x, u, pb.v, w.pk, k, w.T, w_pen, mu, v1, v2);
+        else
+            ok = P::derivs(x, u, pb.v, w.pk, k, w.T, w_pen, mu, v1, v2);
+        double *o1 = w.V1 + (size_t)k * P::NV1 * Bp + b;
+#pragma unroll
+        for (int i = 0; i < P::NV1; i++) o1[i * Bp] = v1[i];
+        if (FULL) {
+            double *o2 = w.V2 + (size_t)k * P::NV2 * Bp + b;
+#pragma unroll
+            for (int i = 0; i < P::NV2_USED; i++) o2[i * Bp] = v2[i];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < P::N_MU_F; i++) mu[i] = w.muF[(size_t)i * Bp + b];
+        double cx[P::NX], cxx[P::NQXX];
+        ok = P::derivs_final(x, pb.v, w.pk, w.T, w.T, w.w_pen_f[b], mu, cx, cxx);
+        double *fd = w.FD + b;
+#pragma unroll
+        for (int i = 0; i < P::NX; i++) fd[i * Bp] = cx[i];
+#pragma unroll
+        for (int i = 0; i < P::NQXX; i++) fd[(P::NX + i) * Bp] = cxx[i];
+    }
+    if (!ok) atomicOr(&w.deriv_fail[b], 1);
+}
+
+/* =====================================================================================================================
+ * K2: backward pass, one lane per problem, incl. the regularisation retry loop and the gradient exit.
+ * ===================================================================================================================== */
+template <class P, bool FULL>
+__global__ void __launch_bounds__(BP_BLOCK) k_backpass(Work w, Opts o, ParamBlock<P> pb, int iter)
+{
+    constexpr int NX = P::NX, NU = P::NU, NQXX = P::NQXX, NQUU = P::NQUU, NQXU = P::NQXU;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= w.B) return;
+    if (w.status[b] != ST_RUNNING) return;
+    if (w.new_deriv[b]) {
+        if (w.deriv_fail[b]) { /* "Calculating derivatives failed": break (iLQG.c:248-251) */
+            finish(w, b, iter, w.bp_done[b] ? 1 : 0);
+            return;
+        }
+        w.new_deriv[b] = 0;
+    }
+    const size_t Bp = w.Bp;
+    const int T = w.T;
+    const int cur = w.cur[b];
+    double lambda = w.lambda[b], dlambda = w.dlambda[b];
+    Dense<P> D;
+    P::consts(pb.v, D);
+
+    double Vx[NX], Vxx[NQXX];
+    double dV0 = 0.0, dV1 = 0.0, g_sum = 0.0;
+    int n_bp = w.n_bp[b];
+    bool done = false;
+    while (!done) {
+        n_bp++;
+#pragma unroll
+        for (int i = 0; i < NX; i++) Vx[i] = w.FD[(size_t)i * Bp + b];
+#pragma unroll
+        for (int i = 0; i < NQXX; i++) Vxx[i] = w.FD[(size_t)(NX + i) * Bp + b];
+        dV0 = 0.0;
+        dV1 = 0.0;
+        g_sum = 0.0;
+        double lk[NU];
+#pragma unroll
+        for (int i = 0; i < NU; i++) lk[i] = 0.0;
+        bool failed = false;
+
+        for (int k = T - 1; k >= 0; k--) {
+            {
+                double v1[P::NV1];
+                const double *i1 = w.V1 + (size_t)k * P::NV1 * Bp + b;
+#pragma unroll
+                for (int i = 0; i < P::NV1; i++) v1[i] = i1[i * Bp];
+                P::unpack(v1, D);
+            }
+            double Qx[NX], Qu[NU], Qxx[NQXX], Quu[NQUU], Qxu[NQXU], QuuF[NQUU], Qxu_reg[NQXU];
+            /* Q-function (back_pass.c:80-131) */
+#pragma unroll
+            for (int i = 0; i < NU; i++) Qu[i] = D.cu[i];
+            add_mul_vec<NX, NU>(Qu, Vx, D.fu);
+#pragma unroll
+            for (int i = 0; i < NX; i++) Qx[i] = D.cx[i];
+            add_mul_vec<NX, NX>(Qx, Vx, D.fx);
+#pragma unroll
+            for (int i = 0; i < NQXU; i++) Qxu[i] = D.cxu[i];
+            add_mul2_tri<NX, NX, NU>(Qxu, Vxx, D.fx, D.fu);
+#pragma unroll
+            for (int i = 0; i < NQUU; i++) Quu[i] = D.cuu[i];
+            add_square_tri<NX, NU>(Quu, Vxx, D.fu);
+#pragma unroll
+            for (int i = 0; i < NQXX; i++) Qxx[i] = D.cxx[i];
+            add_square_tri<NX, NX>(Qxx, Vxx, D.fx);
+            if (FULL) {
+                double v2[P::NV2];
+                const double *i2 = w.V2 + (size_t)k * P::NV2 * Bp + b;
+#pragma unroll
+                for (int i = 0; i < P::NV2_USED; i++) v2[i] = i2[i * Bp];
+                P::add2_Qxu(Vx, v2, pb.v, Qxu);
+                P::add2_Quu(Vx, v2, pb.v, Quu);
+                P::add2_Qxx(Vx, v2, pb.v, Qxx);
+            }
+            /* regularisation (back_pass.c:134-159) */
+#pragma unroll
+            for (int i = 0; i < NQUU; i++) QuuF[i] = Quu[i];
+#pragma unroll
+            for (int i = 0; i < NQXU; i++) Qxu_reg[i] = Qxu[i];
+            if (o.regType == 2) {
+#pragma unroll
+                for (int j = 0; j < NU; j++)
+#pragma unroll
+                    for (int i = 0; i <= j; i++) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int c = 0; c < NU; c++)
+                            acc += D.fu[symtri(c, i)] * D.fu[symtri(c, j)];
+                        QuuF[utri(i, j)] += acc * lambda;
+                    }
+#pragma unroll
+                for (int i = 0; i < NX; i++)
+#pragma unroll
+                    for (int j = 0; j < NU; j++) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int c = 0; c < NX; c++)
+                            acc += D.fx[c + i * NX] * D.fu[(c + j * NU) < NX * NU ? (c + j * NU) : 0];
+                        Qxu_reg[i + j * NX] += acc * lambda;
+                    }
+            }
+            if (o.regType == 1) {
+#pragma unroll
+                for (int i = 0; i < NU; i++) QuuF[utri(i, i)] += lambda;
+            }
+            /* box QP, warm-started from step k+1 (back_pass.c:163-171) */
+            int clamped[NU], n_free;
+            double invH[NQUU];
+            const int qp = box_qp<NU>(QuuF, Qu, D.lower, D.upper, lk, clamped, invH, n_free);
+            if (w.tr_clamp) {
+                int code = (qp & 0xff) << 16;
+#pragma unroll
+                for (int i = 0; i < NU; i++) code |= clamped[i] << (2 * i);
+                w.tr_clamp[(size_t)k * Bp + b] = code;
+            }
+            if (qp < 1) {
+                failed = true;
+                break;
+            }
+            /* gains (back_pass.c:173-201) */
+            double Lk[NU * NX];
+#pragma unroll
+            for (int i = 0; i < NU * NX; i++) Lk[i] = 0.0;
+#pragma unroll
+            for (int i = 0; i < NU; i++) {
+                if (clamped[i]) {
+                    if (P::HAS_HX) {
+#pragma unroll
+                        for (int s = 0; s < NX; s++)
+                            Lk[i + s * NU] -= (clamped[i] == 1) ? D.lower_sign[i] * D.lower_hx[s + i * NX]
+                                                                  : D.upper_sign[i] * D.upper_hx[s + i * NX];
+                    }
+                    continue;
+                }
+#pragma unroll
+                for (int j = 0; j < NU; j++) {
+                    if (!clamped[j]) {
+#pragma unroll
+                        for (int s = 0; s < NX; s++)
+                            Lk[i + s * NU] -= invH[symtri(i, j)] * Qxu_reg[s + j * NX];
+                    } else if (P::HAS_HX) {
+                        double wgt = 0.0;
+#pragma unroll
+                        for (int c = 0; c < NU; c++)
+                            if (!clamped[c])
+                                wgt -= invH[symtri(i, c)] * QuuF[symtri(c, j)];
+#pragma unroll
+                        for (int s = 0; s < NX; s++)
+                            Lk[i + s * NU] -= wgt * ((clamped[j] == 1) ? D.lower_sign[j] * D.lower_hx[s + j * NX]
+                                                                         : D.upper_sign[j] * D.upper_hx[s + j * NX]);
+                    }
+                }
+            }
+            {
+                double *lo = w.l + (size_t)k * NU * Bp + b;
+#pragma unroll
+                for (int i = 0; i < NU; i++) lo[i * Bp] = lk[i];
+                double *Lo = w.Lg + (size_t)k * NU * NX * Bp + b;
+#pragma unroll
+                for (int i = 0; i < NU * NX; i++) Lo[i * Bp] = Lk[i];
+            }
+            /* expected reduction (back_pass.c:204-214) */
+#pragma unroll
+            for (int i = 0; i < NU; i++) dV0 += Qu[i] * lk[i];
+#pragma unroll
+            for (int i = 0; i < NU; i++) {
+                double acc = 0.0;
+#pragma unroll
+                for (int j = 0; j < NU; j++) acc += lk[j] * Quu[symtri(j, i)];
+                dV1 += 0.5 * lk[i] * acc;
+            }
+            /* value function (back_pass.c:217-241) */
+#pragma unroll
+            for (int i = 0; i < NX; i++) Vx[i] = Qx[i];
+            add_mul2_tri<NU, NX, 1>(Vx, Quu, Lk, lk);
+#pragma unroll
+            for (int i = 0; i < NX; i++)
+#pragma unroll
+                for (int j = 0; j < NU; j++) Vx[i] += Lk[j + i * NU] * Qu[j];
+#pragma unroll
+            for (int i = 0; i < NX; i++)
+#pragma unroll
+                for (int j = 0; j < NU; j++) Vx[i] += Qxu[i + j * NX] * lk[j];
+#pragma unroll
+            for (int i = 0; i < NQXX; i++) Vxx[i] = Qxx[i];
+            add_square_tri<NU, NX>(Vxx, Quu, Lk);
+#pragma unroll
+            for (int i = 0; i < NX; i++)
+#pragma unroll
+                for (int j = 0; j < NX; j++)
+#pragma unroll
+                    for (int c = 0; c < NU; c++) {
+                        double term = Lk[c + i * NU] * Qxu[j + c * NX];
+                        if (i == j) term *= 2.0;
+                        Vxx[symtri(i, j)] += term;
+                    }
+            /* gradient measure (back_pass.c:244-251) */
+            {
+                const double *Uc = w.U[cur] + (size_t)k * NU * Bp + b;
+                double gmax = 0.0;
+#pragma unroll
+                for (int i = 0; i < NU; i++) {
+                    const double gi = fabs(lk[i]) / (fabs(Uc[i * Bp]) + 1.0);
+                    if (gi > gmax) gmax = gi;
+                }
+                g_sum += gmax;
+            }
+        }
+        if (failed) {
+            raise_lambda(o, lambda, dlambda);
+            if (lambda > o.lambdaMax) break;
+        } else {
+            done = true;
+        }
+    }
+    w.n_bp[b] = n_bp;
+    w.dV0[b] = dV0;
+    w.dV1[b] = dV1;
+    w.bp_done[b] = done ? 1 : 0;
+    double g_norm = w.g_norm[b];
+    if (done) {
+        g_norm = g_sum / ((double)(T - 1));
+        w.g_norm[b] = g_norm;
+    }
+    if (g_norm < o.tolGrad && lambda < 1e-5) { /* iLQG.c:297-303 */
+        lower_lambda(o, lambda, dlambda);
+        finish(w, b, iter, done ? 1 : 0);
+    } else if (!done) {
+        finish(w, b, iter, 0);
+    }
+    w.lambda[b] = lambda;
+    w.dlambda[b] = dlambda;
+}
+
+/* =====================================================================================================================
+ * K3: rollouts.  MODE 0 = initial rollout of the caller's controls (alpha = 0, clamped; iLQG_mex.c:113-120 and the
+ * first lines of iLQG(), iLQG.c:227-237).  MODE 1 = backtracking line search + accept/reject (line_search.c:33-78,
+ * iLQG.c:306-361).
+ * ===================================================================================================================== */
+template <class P>
+__device__ __forceinline__ bool rollout(const Work &w, const ParamBlock<P> &pb, int b, int from, int to, double alpha,
+                                        double w_pen_l, double w_pen_f, double &csum)
+{
+    constexpr int NX = P::NX, NU = P::NU;
+    const size_t Bp = w.Bp;
+    const int T = w.T;
+    double x[NX], xn[NX], u[NU], mu[P::N_MU_R + P::N_MU_F + 1];
+#pragma unroll
+    for (int i = 0; i < NX; i++) x[i] = w.x0[(size_t)i * Bp + b];
+    csum = 0.0;
+    for (int k = 0; k < T; k++) {
+        const double *Un = w.U[from] + (size_t)k * NU * Bp + b;
+        if (alpha != 0.0) {
+            const double *Xn = w.X[from] + (size_t)k * NX * Bp + b;
+            const double *ln = w.l + (size_t)k * NU * Bp + b;
+            const double *Ln = w.Lg + (size_t)k * NU * NX * Bp + b;
+#pragma unroll
+            for (int j = 0; j < NU; j++) u[j] = Un[j * Bp] + ln[j * Bp] * alpha;
+#pragma unroll
+            for (int i = 0; i < NX; i++) {
+                const double dx = x[i] - Xn[i * Bp];
+#pragma unroll
+                for (int j = 0; j < NU; j++) u[j] += Ln[(j + i * NU) * Bp] * dx;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < NU; j++) u[j] = Un[j * Bp];
+        }
+#pragma unroll
+        for (int i = 0; i < P::N_MU_R; i++) mu[i] = w.muR[((size_t)k * P::N_MU_R + i) * Bp + b];
+        double c;
+        const bool ok = P::step(x, u, pb.v, w.pk, k, T, w_pen_l, mu, xn, c);
+        double *Xo = w.X[to] + (size_t)k * NX * Bp + b;
+        double *Uo = w.U[to] + (size_t)k * NU * Bp + b;
+#pragma unroll
+        for (int i = 0; i < NX; i++) Xo[i * Bp] = x[i];
+#pragma unroll
+        for (int j = 0; j < NU; j++) Uo[j * Bp] = u[j];
+        if (!ok) return false;
+        csum += c;
+#pragma unroll
+        for (int i = 0; i < NX; i++) x[i] = xn[i];
+    }
+    double *Xo = w.X[to] + (size_t)T * NX * Bp + b;
+#pragma unroll
+    for (int i = 0; i < NX; i++) Xo[i * Bp] = x[i];
+#pragma unroll
+    for (int i = 0; i < P::N_MU_F; i++) mu[i] = w.muF[(size_t)i * Bp + b];
+    double c;
+    if (!P::final_cost(x, pb.v, w.pk, T, T, w_pen_f, mu, c)) return false;
+    csum += c;
+    return true;
+}
+
+/* cost-only pass over the nominal trajectory (forward_pass with cost_only = 1) */
+template <class P>
+__device__ __forceinline__ bool cost_pass(const Work &w, const ParamBlock<P> &pb, int b, int buf, double w_pen_l,
+                                          double w_pen_f, double &csum)
+{
+    constexpr int NX = P::NX, NU = P::NU;
+    const size_t Bp = w.Bp;
+    const int T = w.T;
+    double x[NX], u[NU], mu[P::N_MU_R + P::N_MU_F + 1];
+    csum = 0.0;
+    for (int k = 0; k < T; k++) {
+        const double *Xn = w.X[buf] + (size_t)k * NX * Bp + b;
+        const double *Un = w.U[buf] + (size_t)k * NU * Bp + b;
+#pragma unroll
+        for (int i = 0; i < NX; i++) x[i] = Xn[i * Bp];
+#pragma unroll
+        for (int j = 0; j < NU; j++) u[j] = Un[j * Bp];
+#pragma unroll
+        for (int i = 0; i < P::N_MU_R; i++) mu[i] = w.muR[((size_t)k * P::N_MU_R + i) * Bp + b];
+        double c;
+        if (!P::step_cost(x, u, pb.v, w.pk, k, T, w_pen_l, mu, c)) return false;
+        csum += c;
+    }
+    const double *Xn = w.X[buf] + (size_t)T * NX * Bp + b;
+#pragma unroll
+    for (int i = 0; i < NX; i++) x[i] = Xn[i * Bp];
+#pragma unroll
+    for (int i = 0; i < P::N_MU_F; i++) mu[i] = w.muF[(size_t)i * Bp + b];
+    double c;
+    if (!P::final_cost(x, pb.v, w.pk, T, T, w_pen_f, mu, c)) return false;
+    csum += c;
+    return true;
+}
+
+template <class P>
+__global__ void __launch_bounds__(BP_BLOCK) k_init(Work w, Opts o, ParamBlock<P> pb)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= w.B) return;
+    const size_t Bp = w.Bp;
+    const int T = w.T;
+    /* init_multipliers (iLQG_func.tem:364-400) */
+    for (int k = 0; k < T; k++)
+#pragma unroll
+        for (int i = 0; i < P::N_MU_R; i++) {
+            w.muR[((size_t)k * P::N_MU_R + i) * Bp + b] = (i < P::N_MU_LE) ? 0.0 : 1.0;
+            w.lastR[((size_t)k * P::N_MU_R + i) * Bp + b] = 0.0;
+        }
+#pragma unroll
+    for (int i = 0; i < P::N_MU_F; i++) {
+        w.muF[(size_t)i * Bp + b] = (i < P::N_MU_FE) ? 0.0 : 1.0;
+        w.lastF[(size_t)i * Bp + b] = 0.0;
+    }
+    /* the caller's controls sit in buffer 0; roll them out (clamped) into buffer 1, which becomes nominal.
+       The harness-level rollout runs before iLQG() sets the penalty weights, i.e. with whatever the option struct
+       holds: w_pen_l/f are still their zero-initialised values at that point (iLQG_mex.c:24,116). */
+    double csum;
+    const bool ok = rollout<P>(w, pb, b, 0, 1, 0.0, 0.0, 0.0, csum);
+    w.cur[b] = 1;
+    w.cost[b] = csum;
+    w.new_cost[b] = csum;
+    w.dcost[b] = 0.0;
+    w.expected[b] = 0.0;
+    w.g_norm[b] = 0.0;
+    w.dV0[b] = 0.0;
+    w.dV1[b] = 0.0;
+    w.n_ls[b] = 0;
+    w.n_bp[b] = 0;
+    w.bp_done[b] = 0;
+    w.deriv_fail[b] = 0;
+    w.post_mode[b] = POST_NONE;
+    w.iterations[b] = 0;
+    w.result[b] = ok ? 0 : -1;
+    w.status[b] = ok ? ST_RUNNING : ST_DONE;
+    /* first lines of iLQG() (iLQG.c:226-237) */
+    w.lambda[b] = o.lambdaInit;
+    w.dlambda[b] = o.dlambdaInit;
+    w.w_pen_l[b] = o.w_pen_init_l;
+    w.w_pen_f[b] = o.w_pen_init_f;
+    w.new_deriv[b] = 1;
+    if (ok && (P::N_MU_R + P::N_MU_F) > 0) {
+        /* update_multipliers(o, 1): records last_h of step 0 only (running; the early return sits inside the loop,
+           iLQG_func.tem:452) and of the final constraints */
+        double x[P::NX], u[P::NU], mu[P::N_MU_R + P::N_MU_F + 1], hval[P::N_MU_R + P::N_MU_F + 1],
+            mun[P::N_MU_R + P::N_MU_F + 1];
+        if (P::N_MU_R > 0 && T > 0) {
+#pragma unroll
+            for (int i = 0; i < P::NX; i++) x[i] = w.X[1][(size_t)i * Bp + b];
+#pragma unroll
+            for (int i = 0; i < P::NU; i++) u[i] = w.U[1][(size_t)i * Bp + b];
+#pragma unroll
+            for (int i = 0; i < P::N_MU_R; i++) mu[i] = w.muR[(size_t)i * Bp + b];
+            P::mult_running(x, u, pb.v, w.pk, 0, T, o.w_pen_init_l, mu, hval, mun);
+#pragma unroll
+            for (int i = 0; i < P::N_MU_R; i++) w.lastR[(size_t)i * Bp + b] = hval[i];
+        }
+        if (P::N_MU_F > 0) {
+#pragma unroll
+            for (int i = 0; i < P::NX; i++) x[i] = w.X[1][((size_t)T * P::NX + i) * Bp + b];
+#pragma unroll
+            for (int i = 0; i < P::N_MU_F; i++) mu[i] = w.muF[(size_t)i * Bp + b];
+            P::mult_final(x, pb.v, w.pk, T, T, o.w_pen_init_f, mu, hval, mun);
+#pragma unroll
+            for (int i = 0; i < P::N_MU_F; i++) w.lastF[(size_t)i * Bp + b] = hval[i];
+        }
+    }
+}
+
+template <class P>
+__global__ void __launch_bounds__(BP_BLOCK) k_linesearch(Work w, Opts o, ParamBlock<P> pb, int iter)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= w.B) return;
+    if (w.status[b] != ST_RUNNING) return;
+    const size_t Bp = w.Bp;
+    const int cur = w.cur[b];
+    const double cost = w.cost[b], dV0 = w.dV0[b], dV1 = w.dV1[b];
+    double w_pen_l = w.w_pen_l[b], w_pen_f = w.w_pen_f[b];
+    double lambda = w.lambda[b], dlambda = w.dlambda[b];
+    double cnew = w.new_cost[b], dcost = w.dcost[b], expected = w.expected[b];
+    if (w.tr_lambda) w.tr_lambda[(size_t)iter * Bp + b] = lambda;
+    w.n_ls[b] += 1;
+
+    int tried = 0;
+    bool accepted = false;
+    for (tried = 0; tried < o.n_alpha; tried++) {
+        const double alpha = o.alpha[tried];
+        double csum;
+        if (!rollout<P>(w, pb, b, cur, cur ^ 1, alpha, w_pen_l, w_pen_f, csum)) {
+            cnew = csum;
+            continue;
+        }
+        cnew = csum;
+        dcost = cost - cnew;
+        expected = -alpha * (dV0 + alpha * dV1);
+        const double z = (expected > 0) ? dcost / expected : 0.0;
+        if (z > o.zMin) {
+            accepted = true;
+            break;
+        }
+    }
+    if (w.tr_alpha) w.tr_alpha[(size_t)iter * Bp + b] = tried + 1;
+    if (w.tr_newcost) w.tr_newcost[(size_t)iter * Bp + b] = cnew;
+    w.new_cost[b] = cnew;
+    w.dcost[b] = dcost;
+    w.expected[b] = expected;
+
+    int post = POST_NONE;
+    if (accepted) { /* iLQG.c:311-338 */
+        lower_lambda(o, lambda, dlambda);
+        w.cur[b] = cur ^ 1;
+        w.cost[b] = cnew;
+        w.new_deriv[b] = 1;
+        if (dcost < o.tolFun)
+            finish(w, b, iter, 1);
+        else
+            post = POST_MULT;
+    } else { /* iLQG.c:340-361 */
+        raise_lambda(o, lambda, dlambda);
+        if (o.w_pen_fact2 > 1.0) {
+            w_pen_l = dmin(o.w_pen_max_l, w_pen_l * o.w_pen_fact2);
+            w_pen_f = dmin(o.w_pen_max_f, w_pen_f * o.w_pen_fact2);
+            w.w_pen_l[b] = w_pen_l;
+            w.w_pen_f[b] = w_pen_f;
+            post = POST_COST;
+        }
+        if (lambda > o.lambdaMax)
+            finish(w, b, iter, 1); /* backPassDone is set and iter < max_iter: the reference returns 1 here */
+    }
+    w.post_mode[b] = post;
+    w.lambda[b] = lambda;
+    w.dlambda[b] = dlambda;
+}
+
+/* K5: update_multipliers(o, 0) and the cost-only pass that follows an accepted step, or the cost-only pass after a
+ * rejected step whose penalty weights grew (iLQG.c:337-338, 345-349).  Only launched for problems with multipliers. */
+template <class P>
+__global__ void __launch_bounds__(BP_BLOCK) k_post(Work w, Opts o, ParamBlock<P> pb)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= w.B) return;
+    const int mode = w.post_mode[b];
+    if (mode == POST_NONE) return;
+    w.post_mode[b] = POST_NONE;
+    constexpr int NX = P::NX, NU = P::NU, NR = P::N_MU_R, NF = P::N_MU_F;
+    const size_t Bp = w.Bp;
+    const int T = w.T;
+    const int cur = w.cur[b];
+    double w_pen_l = w.w_pen_l[b], w_pen_f = w.w_pen_f[b];
+    if (mode == POST_MULT) {
+        double x[NX], u[NU], mu[NR + NF + 1], hval[NR + NF + 1], mun[NR + NF + 1];
+        if (NR > 0) {
+            bool increase = false;
+            for (int k = 0; k < T; k++) {
+                const double *Xn = w.X[cur] + (size_t)k * NX * Bp + b;
+                const double *Un = w.U[cur] + (size_t)k * NU * Bp + b;
+#pragma unroll
+                for (int i = 0; i < NX; i++) x[i] = Xn[i * Bp];
+#pragma unroll
+                for (int j = 0; j < NU; j++) u[j] = Un[j * Bp];
+#pragma unroll
+                for (int i = 0; i < NR; i++) mu[i] = w.muR[((size_t)k * NR + i) * Bp + b];
+                P::mult_running(x, u, pb.v, w.pk, k, T, w_pen_l, mu, hval, mun);
+#pragma unroll
+                for (int i = 0; i < NR; i++) {
+                    double *last = &w.lastR[((size_t)k * NR + i) * Bp + b];
+                    if (i < P::N_MU_LE) {
+                        if (fabs(hval[i]) > o.tolConstraint && o.w_pen_fact1 * fabs(hval[i]) > fabs(*last)) increase = true;
+                    } else {
+                        if (hval[i] > o.tolConstraint && o.w_pen_fact1 * hval[i] > *last) increase = true;
+                    }
+                    *last = hval[i];
+                    w.muR[((size_t)k * NR + i) * Bp + b] = mun[i];
+                }
+            }
+            if (increase) w_pen_l = dmin(o.w_pen_max_l, w_pen_l * o.w_pen_fact1);
+        }
+        if (NF > 0) {
+            bool increase = false;
+            const double *Xn = w.X[cur] + (size_t)T * NX * Bp + b;
+#pragma unroll
+            for (int i = 0; i < NX; i++) x[i] = Xn[i * Bp];
+#pragma unroll
+            for (int i = 0; i < NF; i++) mu[i] = w.muF[(size_t)i * Bp + b];
+            P::mult_final(x, pb.v, w.pk, T, T, w_pen_f, mu, hval, mun);
+#pragma unroll
+            for (int i = 0; i < NF; i++) {
+                double *last = &w.lastF[(size_t)i * Bp + b];
+                if (i < P::N_MU_FE) {
+                    if (fabs(hval[i]) > o.tolConstraint && o.w_pen_fact1 * fabs(hval[i]) > fabs(*last)) increase = true;
+                } else {
+                    if (hval[i] > o.tolConstraint && o.w_pen_fact1 * hval[i] > *last) increase = true;
+                }
+                *last = hval[i];
+                w.muF[(size_t)i * Bp + b] = mun[i];
+            }
+            if (increase) w_pen_f = dmin(o.w_pen_max_f, w_pen_f * o.w_pen_fact1);
+        }
+        w.w_pen_l[b] = w_pen_l;
+        w.w_pen_f[b] = w_pen_f;
+    }
+    double csum;
+    cost_pass<P>(w, pb, b, cur, w_pen_l, w_pen_f, csum);
+    w.cost[b] = csum;
+}
+
+/* after the last pass: problems still running hit the iteration limit (iLQG.c:365-377) */
+__global__ void k_finalize(Work w, int max_iter)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= w.B) return;
+    if (w.status[b] == ST_RUNNING) {
+        w.status[b] = ST_DONE;
+        w.iterations[b] = max_iter;
+        w.result[b] = 0;
+    }
+}
+
+__global__ void k_count_active(Work w, int *out)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    int a = (b < w.B) && (w.status[b] == ST_RUNNING);
+    a = __syncthreads_count(a);
+    if (threadIdx.x == 0 && a) atomicAdd(out, a);
+}
+
+/* layout changes between the caller's problem-major arrays and the device's [k][i][b] arrays */
+__global__ void k_scatter(const double *src /*[B][n_k][n_i]*/, double *dst /*[n_k][n_i][Bp]*/, int B, int Bp, int n_k, int n_i)
+{
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t per = (size_t)n_k * n_i;
+    if (e >= per * B) return;
+    /* thread order follows dst (b fastest) so the stores coalesce; loads go through L2 */
+    const size_t b = e % B, ki = e / B;
+    dst[ki * Bp + b] = src[b * per + ki];
+}
+
+__global__ void k_gather(const double *src /*[n_k][n_i][Bp]*/, double *dst /*[B][n_k][n_i]*/, const int *sel /* per-b buffer select or null */,
+                         const double *src_alt, int B, int Bp, int n_k, int n_i)
+{
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t per = (size_t)n_k * n_i;
+    if (e >= per * B) return;
+    const size_t b = e % B, ki = e / B;
+    const double *s = (sel && sel[b]) ? src_alt : src;
+    dst[b * per + ki] = s[ki * Bp + b];
+}
+
+} /* namespace ilqg */

@@ -1,0 +1,35 @@
+/* ilqg_work.h -- plain-C descriptors shared by the C host layer (ilqg_host.c) and the CUDA layer (ilqg_cuda.cu).
+ * Everything a kernel needs travels by value in these two structs (kernel parameter space), never via globals. */
+#ifndef ILQG_WORK_H
+#define ILQG_WORK_H
+
+#define ILQG_MAX_ALPHA 16
+
+/* run-time options: the numeric subset of tOptSet the solve loop reads (reference iLQG.h:45-68) */
+typedef struct ilqg_opts {
+    double alpha[ILQG_MAX_ALPHA];
+    int n_alpha;
+    double lambdaMax, lambdaMin, lambdaInit, dlambdaInit, lambdaFactor;
+    double tolGrad, tolFun, tolConstraint, zMin;
+    double w_pen_init_l, w_pen_init_f, w_pen_max_l, w_pen_max_f, w_pen_fact1, w_pen_fact2;
+    int regType, max_iter;
+} ilqg_opts;
+
+/* device workspace of one batch; all arrays are [..][Bp] with the problem index fastest */
+typedef struct ilqg_work {
+    int B, Bp, T;
+    double *X[2], *U[2];       /* two trajectory buffers: x [T+1][NX][Bp], u [T][NU][Bp]; cur[b] says which is nominal */
+    double *x0;                /* [NX][Bp] */
+    double *l, *Lg;            /* open-loop term [T][NU][Bp], feedback gains [T][NU*NX][Bp] */
+    double *V1, *V2, *FD;      /* time-varying derivative entries [T][NV1][Bp], [T][NV2][Bp]; final cx,cxx [NX+NQXX][Bp] */
+    double *muR, *lastR, *muF, *lastF;
+    const double *const *pk;   /* [k]-indexed parameters (device pointers), or null */
+    double *cost, *new_cost, *dcost, *expected, *lambda, *dlambda, *g_norm, *dV0, *dV1, *w_pen_l, *w_pen_f;
+    int *cur, *status, *new_deriv, *deriv_fail, *iterations, *result, *n_ls, *n_bp, *bp_done, *post_mode;
+    /* optional traces for parity tests (null when disabled) */
+    double *tr_lambda, *tr_newcost; /* [max_iter][Bp] */
+    int *tr_alpha;                  /* [max_iter][Bp] */
+    int *tr_clamp;                  /* [T][Bp]: is_clamped of the last back pass, 2 bits per input, QP code << 16 */
+} ilqg_work;
+
+#endif

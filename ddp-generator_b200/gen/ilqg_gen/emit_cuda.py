@@ -53,7 +53,7 @@ class CuNames:
         return self.map[s]
 
 
-def render(sc: Scope, names, tname, indent="        "):
+def render(sc: Scope, names, tname, indent="        ", guards=True):
     out = []
     for it in sc.items:
         if it[0] == "tmp":
@@ -61,7 +61,7 @@ def render(sc: Scope, names, tname, indent="        "):
         elif it[0] == "out":
             lhs, decl = tname(it[1])
             out.append(f"{indent}{decl}{lhs} = {render_operand(it[2], names)};")
-            if it[3]:
+            if it[3] and guards:
                 out.append(f"{indent}ok &= dm_isfinite({lhs});")
         elif it[0] == "raw":
             out.append(it[1](names, indent))
@@ -283,7 +283,7 @@ def emit_device(m, struct_name) -> str:
             if not e.time_var:
                 sc.out(("arr", f"D.{key}", e.idx), e.expr, False)
     o.append("    template <class DT> __device__ __forceinline__ static void consts(const double *p, DT &D) {\n        (void)p;")
-    o.append(render(sc, NR, aux_t))
+    o.append(render(sc, NR, aux_t, guards=False))
     if m.has_hx is False:
         pass
     o.append("    }\n")
@@ -318,7 +318,7 @@ def emit_device(m, struct_name) -> str:
             if not terms:
                 continue
             ls.append((j, terms))
-        pre = render(sck, NR, aux_t)
+        pre = render(sck, NR, aux_t, guards=False)
         body = []
         for j, terms in ls:
             body.append("        { double d1 = 0.0;" + "".join(f" d1 += Vx[{i}] * {t};" for i, t in terms) + f" {outname}[{j}] += d1; }}")
@@ -351,7 +351,7 @@ def emit_device(m, struct_name) -> str:
                     sc.out(("var", f"const double nI{off}"), r["next_I"], False)
                     sc.raw(lambda names, ind, off=off: f"{ind}mu_next[{off}] = (hval[{off}] >= 0) ? nA{off} : nI{off};")
                 off += 1
-        return render(sc, NN, aux_t)
+        return render(sc, NN, aux_t, guards=False)
 
     o.append("    /* constraint values and updated multipliers; is_ineq[i] tells which test update_multipliers applies */")
     o.append(f"    __device__ __forceinline__ static void mult_running(const double *x, const double *u, {ARGS}, double *hval, double *mu_next) {{")

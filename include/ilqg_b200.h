@@ -1,0 +1,95 @@
+/* ilqg_b200.h -- C ABI of the B200 batched iLQG / control-limited DDP solver.
+ *
+ * One shared library per generated problem and FULL_DDP setting (libilqg_b200_<problem>_ddp<0|1>.so), exactly as
+ * the reference builds one mex per problem (make_iLQG.m:65-86).  All entry points are extern "C", take plain
+ * pointers and sizes, and run on the GPU: there is no CPU fallback -- creation fails if no CUDA device is usable.
+ *
+ * What each entry point replaces in the reference (file:line in jgeisler0303/DDP-Generator):
+ *   ilqgb_create / ilqgb_destroy   allocation of trajectories/multipliers by the caller, iLQG_mex.c:100-103, 141-143
+ *   ilqgb_standard_parameters      standard_parameters(), iLQG.c:57-78
+ *   ilqgb_set_opt                  setOptParam(), iLQG.c:91-216 (same names, validation and messages)
+ *   ilqgb_set_param                binding of the parameter struct by name, iLQG_mex.c:70-84 / paramdesc, iLQG.h:97-99
+ *   ilqgb_upload                   o.x0, copy of u_nom into the nominal trajectory, iLQG_mex.c:55-56, 113-115
+ *   ilqgb_start                    init_opt + initial rollout + makeCandidateNominal, iLQG_mex.c:108-120, and the
+ *                                  first lines of iLQG(), iLQG.c:226-237
+ *   ilqgb_iterate                  passes of the iLQG() loop, iLQG.c:239-363, for every problem of the batch
+ *   ilqgb_finish                   iLQG.c:365-378 (iteration-limit bookkeeping)
+ *   ilqgb_solve                    = start + iterate(max_iter) + finish: the whole iLQG() call for B problems
+ *   ilqgb_download                 copy-out of x, u, cost, iLQG_mex.c:127-137, plus iterations / return value
+ *   ilqgb_phase_*                  calc_derivs / back_pass / line_search on their own (iLQG.h:83, back_pass.h:7,
+ *                                  line_search.h:6) for phase-level parity tests
+ *   ilqgb_get / ilqgb_get_int      read-back of any per-problem field (tOptSet / trajEl_t members)
+ * The single-problem drop-in (iLQG(tOptSet*) etc., include/ilqg_compat.h) is layered on these.
+ */
+#ifndef ILQG_B200_H
+#define ILQG_B200_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ilqgb_handle ilqgb_handle;
+
+enum {
+    ILQGB_TRACE = 1,  /* keep per-iteration lambda / alpha / cost and per-step active sets (parity tests) */
+    ILQGB_TIMING = 2  /* record CUDA events around every kernel launch (bench roofline) */
+};
+
+/* static facts of this library build */
+const char *ilqgb_problem_name(void);
+int ilqgb_nx(void);
+int ilqgb_nu(void);
+int ilqgb_full_ddp(void);
+int ilqgb_n_params(void);
+const char *ilqgb_param_name(int i);
+int ilqgb_param_size(int i); /* 1, k > 1, or -1: one value per timestep (n_hor + 1) */
+int ilqgb_device_count(void);
+int ilqgb_deriv_doubles_per_step(void); /* time-varying derivative doubles the derivative kernel stores per step */
+
+/* lifecycle; `stream` may be NULL (the handle then owns a stream) or a cudaStream_t of the caller */
+ilqgb_handle *ilqgb_create(int device, int batch, int n_hor, int flags, void *stream);
+void ilqgb_destroy(ilqgb_handle *h);
+const char *ilqgb_last_error(const ilqgb_handle *h); /* h may be NULL for creation errors */
+
+/* options and parameters (shared by the whole batch) */
+void ilqgb_standard_parameters(ilqgb_handle *h);
+const char *ilqgb_set_opt(ilqgb_handle *h, const char *name, const double *value, int n); /* NULL = ok */
+int ilqgb_set_param(ilqgb_handle *h, int index, const double *value, int n);
+
+/* host -> device: x0 [batch][nx], u_nom [batch][n_hor][nu] (problem-major, as a caller holds them) */
+int ilqgb_upload(ilqgb_handle *h, const double *x0, const double *u_nom);
+
+/* the solve, asynchronous on the handle's stream */
+int ilqgb_start(ilqgb_handle *h);
+int ilqgb_iterate(ilqgb_handle *h, int n_passes); /* returns passes actually launched (stops when none is running) */
+int ilqgb_finish(ilqgb_handle *h);
+int ilqgb_solve(ilqgb_handle *h);
+int ilqgb_sync(ilqgb_handle *h);
+int ilqgb_active(ilqgb_handle *h); /* problems still running (synchronises) */
+
+/* device -> host; any pointer may be NULL. x [batch][n_hor+1][nx], u [batch][n_hor][nu] */
+int ilqgb_download(ilqgb_handle *h, double *x, double *u, double *cost, int *iterations, int *result,
+                   int *n_linesearch);
+
+/* single phases on the current nominal trajectories of all running problems */
+int ilqgb_phase_derivs(ilqgb_handle *h);
+int ilqgb_phase_backpass(ilqgb_handle *h);
+int ilqgb_phase_linesearch(ilqgb_handle *h);
+
+/* field read-back (synchronises). Per-problem scalars: "cost" "new_cost" "dcost" "expected" "lambda" "dlambda"
+ * "g_norm" "dV0" "dV1" "w_pen_l" "w_pen_f" -> [batch].  Trajectory fields, problem-major [batch][k][i]:
+ * "x" "u" (nominal), "l" "L" "v1" (time-varying derivative entries) "v2" "fd" (final cx,cxx) "mu_f" "mu_r";
+ * traces (ILQGB_TRACE): "tr_lambda" "tr_newcost" -> [batch][max_iter].  Returns doubles written, <0 on error. */
+long ilqgb_get(ilqgb_handle *h, const char *field, double *out);
+/* "iterations" "result" "status" "n_linesearch" "n_backpass" "cur" -> [batch]; "tr_alpha" -> [batch][max_iter];
+ * "tr_clamp" -> [batch][n_hor] (2 bits per input: 0 free, 1 lower, 2 upper; QP return code in bits 16..23) */
+long ilqgb_get_int(ilqgb_handle *h, const char *field, int *out);
+
+/* accumulated device time per kernel class since the last reset (ILQGB_TIMING): ms[4] / launches[4] in the
+ * order derivs, backpass, linesearch, post */
+int ilqgb_timing(ilqgb_handle *h, double *ms, long *launches, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
