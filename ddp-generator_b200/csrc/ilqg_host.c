@@ -43,6 +43,7 @@ struct ilqgb_handle {
     int n_ev, cap_ev, n_ev_created;
     double t_ms[TC_N];
     long t_n[TC_N];
+    long n_launches;       /* kernels launched since creation */
     char err[256];
 };
 
@@ -276,6 +277,8 @@ ilqgb_handle *ilqgb_create(int device, int batch, int n_hor, int flags, void *st
         DALLOC(w->n_bp, int, Bp);
         DALLOC(w->bp_done, int, Bp);
         DALLOC(w->post_mode, int, Bp);
+        DALLOC(w->n_dv, int, Bp);
+        DALLOC(w->n_roll, int, Bp);
         ilqgk_memset(w->status, 0, sizeof(int) * Bp, h->stream);
         ilqgk_memset(w->cur, 0, sizeof(int) * Bp, h->stream);
         if (flags & ILQGB_TRACE) {
@@ -346,6 +349,7 @@ int ilqgb_upload(ilqgb_handle *h, const double *x0, const double *u_nom)
     if (ilqgk_h2d(h->d_stage, u_nom, sizeof(double) * B * T * nu, h->stream)) return failk(h);
     if (ilqgk_h2d(h->d_stage + B * T * nu, x0, sizeof(double) * B * nx, h->stream)) return failk(h);
     if (ilqgk_launch_scatter(h->d_stage, h->w.U[0], h->B, h->Bp, h->T, h->d.nu, h->stream)) return failk(h);
+    h->n_launches += 2;
     if (ilqgk_launch_scatter(h->d_stage + B * T * nu, h->w.x0, h->B, h->Bp, 1, h->d.nx, h->stream)) return failk(h);
     h->started = 0;
     return 0;
@@ -357,6 +361,7 @@ static int gather_to_host(ilqgb_handle *h, const double *src, const double *alt,
     if (!n) return 0;
     if (ensure_stage(h, n)) return -1;
     if (ilqgk_launch_gather(src, alt, sel, h->d_stage, h->B, h->Bp, n_k, n_i, h->stream)) return failk(h);
+    h->n_launches++;
     if (ilqgk_d2h(out, h->d_stage, sizeof(double) * n, h->stream)) return failk(h);
     return 0;
 }
@@ -437,6 +442,7 @@ int ilqgb_start(ilqgb_handle *h)
     if (ilqgk_set_device(h->device)) return failk(h);
     if (ensure_traces(h)) return -1;
     if (ilqgk_launch_init(&h->w, &h->o, h->params, h->stream)) return failk(h);
+    h->n_launches++;
     h->iter = 0;
     h->started = 1;
     return 0;
@@ -448,20 +454,24 @@ static int launch_pass(ilqgb_handle *h, int do_derivs, int do_back, int do_ls)
     if (do_derivs) {
         p = timing_begin(h, TC_DERIVS);
         if (ilqgk_launch_derivs(&h->w, h->params, h->stream)) return failk(h);
+        h->n_launches++;
         timing_end(h, p);
     }
     if (do_back) {
         p = timing_begin(h, TC_BACKPASS);
         if (ilqgk_launch_backpass(&h->w, &h->o, h->params, h->iter, h->stream)) return failk(h);
+        h->n_launches++;
         timing_end(h, p);
     }
     if (do_ls) {
         p = timing_begin(h, TC_LINESEARCH);
         if (ilqgk_launch_linesearch(&h->w, &h->o, h->params, h->iter, h->stream)) return failk(h);
+        h->n_launches++;
         timing_end(h, p);
         if (ilqgk_has_post()) {
             p = timing_begin(h, TC_POST);
             if (ilqgk_launch_post(&h->w, &h->o, h->params, h->stream)) return failk(h);
+            h->n_launches++;
             timing_end(h, p);
         }
     }
@@ -472,6 +482,7 @@ int ilqgb_active(ilqgb_handle *h)
 {
     if (ilqgk_set_device(h->device)) return failk(h);
     if (ilqgk_launch_count_active(&h->w, h->d_counter, h->stream)) return failk(h);
+    h->n_launches++;
     if (ilqgk_d2h(h->h_counter, h->d_counter, sizeof(int), h->stream)) return failk(h);
     if (ilqgk_stream_sync(h->stream)) return failk(h);
     return *h->h_counter;
@@ -517,6 +528,8 @@ int ilqgb_solve(ilqgb_handle *h)
     if (ilqgk_launch_finalize(&h->w, h->o.max_iter, h->stream)) return failk(h);
     return 0;
 }
+
+long ilqgb_launch_count(const ilqgb_handle *h) { return h->n_launches; }
 
 int ilqgb_sync(ilqgb_handle *h)
 {
@@ -586,6 +599,8 @@ long ilqgb_get_int(ilqgb_handle *h, const char *f, int *out)
     else if (!strcmp(f, "n_linesearch")) scal = w->n_ls;
     else if (!strcmp(f, "n_backpass")) scal = w->n_bp;
     else if (!strcmp(f, "cur")) scal = w->cur;
+    else if (!strcmp(f, "n_derivs")) scal = w->n_dv;
+    else if (!strcmp(f, "n_rollouts")) scal = w->n_roll;
     if (scal) {
         if (ilqgk_d2h(out, scal, sizeof(int) * B, h->stream) || ilqgk_stream_sync(h->stream)) return failk(h);
         return (long)B;

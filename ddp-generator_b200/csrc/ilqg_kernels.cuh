@@ -392,6 +392,7 @@ __global__ void __launch_bounds__(BP_BLOCK) k_backpass(Work w, Opts o, ParamBloc
             return;
         }
         w.new_deriv[b] = 0;
+        w.n_dv[b] += 1;
     }
     const size_t Bp = w.Bp;
     const int T = w.T;
@@ -740,6 +741,8 @@ __global__ void __launch_bounds__(BP_BLOCK) k_init(Work w, Opts o, ParamBlock<P>
     w.dV1[b] = 0.0;
     w.n_ls[b] = 0;
     w.n_bp[b] = 0;
+    w.n_dv[b] = 0;
+    w.n_roll[b] = 0;
     w.bp_done[b] = 0;
     w.deriv_fail[b] = 0;
     w.post_mode[b] = POST_NONE;
@@ -813,6 +816,7 @@ __global__ void __launch_bounds__(BP_BLOCK) k_linesearch(Work w, Opts o, ParamBl
             break;
         }
     }
+    w.n_roll[b] += (tried < o.n_alpha) ? tried + 1 : o.n_alpha;
     if (w.tr_alpha) w.tr_alpha[(size_t)iter * Bp + b] = tried + 1;
     if (w.tr_newcost) w.tr_newcost[(size_t)iter * Bp + b] = cnew;
     w.new_cost[b] = cnew;

@@ -26,6 +26,7 @@ typedef struct ilqg_work {
     const double *const *pk;   /* [k]-indexed parameters (device pointers), or null */
     double *cost, *new_cost, *dcost, *expected, *lambda, *dlambda, *g_norm, *dV0, *dV1, *w_pen_l, *w_pen_f;
     int *cur, *status, *new_deriv, *deriv_fail, *iterations, *result, *n_ls, *n_bp, *bp_done, *post_mode;
+    int *n_dv, *n_roll;        /* work counters: derivative sweeps consumed, rollouts tried (bench roofline accounting) */
     /* optional traces for parity tests (null when disabled) */
     double *tr_lambda, *tr_newcost; /* [max_iter][Bp] */
     int *tr_alpha;                  /* [max_iter][Bp] */

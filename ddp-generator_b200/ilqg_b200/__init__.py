@@ -74,6 +74,8 @@ class Library:
         L.ilqgb_get_int.restype = C.c_long
         L.ilqgb_get_int.argtypes = [vp, cp, dp]
         L.ilqgb_timing.argtypes = [vp, dp, dp, ci]
+        L.ilqgb_launch_count.restype = C.c_long
+        L.ilqgb_launch_count.argtypes = [vp]
         self.problem = L.ilqgb_problem_name().decode()
         self.nx, self.nu = L.ilqgb_nx(), L.ilqgb_nu()
         self.full_ddp = L.ilqgb_full_ddp()
@@ -204,6 +206,9 @@ class BatchSolver:
         n = self._chk(self.lib.ilqgb_get_int(self.h, field.encode(), _ptr(buf)))
         out = buf[:n].copy()
         return out.reshape(self.B, -1) if n > self.B else out
+
+    def launch_count(self):
+        return int(self.lib.ilqgb_launch_count(self.h))
 
     def timing(self, reset=True):
         ms = np.zeros(4)
