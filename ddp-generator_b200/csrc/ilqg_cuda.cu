@@ -42,6 +42,7 @@ void ilqgk_dims(ilqgk_dims_t *d)
     d->nv1 = P::NV1; d->nv2 = P::NV2; d->npf = P::NPF_USED; d->nkp = P::NKP;
     d->n_mu_r = P::N_MU_R; d->n_mu_f = P::N_MU_F; d->n_mu_le = P::N_MU_LE; d->n_mu_fe = P::N_MU_FE;
     d->full_ddp = FULL_DDP; d->has_hx = P::HAS_HX ? 1 : 0;
+    d->rxu = Rec<P>::RXU; d->rll = Rec<P>::RLL;
 }
 const char *ilqgk_problem_name(void) { return P::name(); }
 int ilqgk_param_count(void) { return P::param_count(); }
@@ -88,8 +89,15 @@ int ilqgk_launch_backpass(const ilqg_work *w, const ilqg_opts *o, const double *
 
 int ilqgk_launch_linesearch(const ilqg_work *w, const ilqg_opts *o, const double *params, int iter, void *stream)
 {
-    k_linesearch<P><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, make_pb(params), iter);
-    return check(cudaGetLastError(), "k_linesearch");
+    /* one launch per alpha; rounds > 0 read their problem list and count from device memory, so no host round trip.
+       Their grids are sized for the worst case and surplus blocks exit at once. */
+    if (check(cudaMemsetAsync(w->ls_count, 0, sizeof(int) * (ILQG_MAX_ALPHA + 2), (cudaStream_t)stream), "memset ls_count")) return -1;
+    const ParamBlock<P> pb = make_pb(params);
+    for (int r = 0; r < o->n_alpha; r++) {
+        k_ls_round<P><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, pb, iter, r);
+        if (check(cudaGetLastError(), "k_ls_round")) return -1;
+    }
+    return 0;
 }
 
 int ilqgk_launch_post(const ilqg_work *w, const ilqg_opts *o, const double *params, void *stream)
@@ -114,19 +122,23 @@ int ilqgk_launch_count_active(const ilqg_work *w, int *d_counter, void *stream)
     return check(cudaGetLastError(), "k_count_active");
 }
 
-int ilqgk_launch_scatter(const double *src, double *dst, int B, int Bp, int n_k, int n_i, void *stream)
+int ilqgk_launch_scatter(const double *src, double *dst, int B, int n_k, int n_i, long long stride_k, long long stride_b,
+                         long long stride_i, long long off, void *stream)
 {
     const size_t n = (size_t)B * n_k * n_i;
     if (!n) return 0;
-    k_scatter<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, dst, B, Bp, n_k, n_i);
+    const Layout L = {stride_k, stride_b, stride_i, off};
+    k_scatter<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, dst, B, n_k, n_i, L);
     return check(cudaGetLastError(), "k_scatter");
 }
 
-int ilqgk_launch_gather(const double *src, const double *src_alt, const int *sel, double *dst, int B, int Bp, int n_k, int n_i, void *stream)
+int ilqgk_launch_gather(const double *src, const double *src_alt, const int *sel, double *dst, int B, int n_k, int n_i,
+                        long long stride_k, long long stride_b, long long stride_i, long long off, void *stream)
 {
     const size_t n = (size_t)B * n_k * n_i;
     if (!n) return 0;
-    k_gather<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, dst, sel, src_alt, B, Bp, n_k, n_i);
+    const Layout L = {stride_k, stride_b, stride_i, off};
+    k_gather<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, src_alt, sel, dst, B, n_k, n_i, L);
     return check(cudaGetLastError(), "k_gather");
 }
 

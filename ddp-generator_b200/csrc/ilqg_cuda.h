@@ -9,7 +9,7 @@ extern "C" {
 #endif
 
 typedef struct ilqgk_dims_t {
-    int nx, nu, nqxx, nquu, nqxu, nv1, nv2, npf, nkp, n_mu_r, n_mu_f, n_mu_le, n_mu_fe, full_ddp, has_hx;
+    int nx, nu, nqxx, nquu, nqxu, nv1, nv2, npf, nkp, n_mu_r, n_mu_f, n_mu_le, n_mu_fe, full_ddp, has_hx, rxu, rll;
 } ilqgk_dims_t;
 
 const char *ilqgk_last_error(void);
@@ -44,8 +44,11 @@ int ilqgk_launch_post(const ilqg_work *w, const ilqg_opts *o, const double *para
 int ilqgk_has_post(void);
 int ilqgk_launch_finalize(const ilqg_work *w, int max_iter, void *stream);
 int ilqgk_launch_count_active(const ilqg_work *w, int *d_counter, void *stream);
-int ilqgk_launch_scatter(const double *src, double *dst, int B, int Bp, int n_k, int n_i, void *stream);
-int ilqgk_launch_gather(const double *src, const double *src_alt, const int *sel, double *dst, int B, int Bp, int n_k, int n_i, void *stream);
+/* [B][n_k][n_i] (host order) <-> device element (k, b, i) at base[k*stride_k + b*stride_b + i*stride_i + off] */
+int ilqgk_launch_scatter(const double *src, double *dst, int B, int n_k, int n_i, long long stride_k, long long stride_b,
+                         long long stride_i, long long off, void *stream);
+int ilqgk_launch_gather(const double *src, const double *src_alt, const int *sel, double *dst, int B, int n_k, int n_i,
+                        long long stride_k, long long stride_b, long long stride_i, long long off, void *stream);
 
 #ifdef __cplusplus
 }

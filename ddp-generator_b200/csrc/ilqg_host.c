@@ -242,12 +242,11 @@ ilqgb_handle *ilqgb_create(int device, int batch, int n_hor, int flags, void *st
         w->Bp = h->Bp;
         w->T = n_hor;
         for (i = 0; i < 2; i++) {
-            DALLOC(w->X[i], double, (T + 1) * d->nx * Bp);
-            DALLOC(w->U[i], double, T * d->nu * Bp);
+            DALLOC(w->XU[i], double, (T + 1) * Bp * d->rxu);
+            ilqgk_memset(w->XU[i], 0, sizeof(double) * (T + 1) * Bp * d->rxu, h->stream);
         }
         DALLOC(w->x0, double, d->nx * Bp);
-        DALLOC(w->l, double, T * d->nu * Bp);
-        DALLOC(w->Lg, double, T * d->nu * d->nx * Bp);
+        DALLOC(w->LL, double, T * Bp * d->rll);
         DALLOC(w->V1, double, T * d->nv1 * Bp);
         DALLOC(w->V2, double, d->full_ddp ? T * d->nv2 * Bp : 1);
         DALLOC(w->FD, double, (d->nx + d->nqxx) * Bp);
@@ -277,6 +276,9 @@ ilqgb_handle *ilqgb_create(int device, int batch, int n_hor, int flags, void *st
         DALLOC(w->n_bp, int, Bp);
         DALLOC(w->bp_done, int, Bp);
         DALLOC(w->post_mode, int, Bp);
+        DALLOC(w->ls_list[0], int, Bp);
+        DALLOC(w->ls_list[1], int, Bp);
+        DALLOC(w->ls_count, int, ILQG_MAX_ALPHA + 2);
         DALLOC(w->n_dv, int, Bp);
         DALLOC(w->n_roll, int, Bp);
         ilqgk_memset(w->status, 0, sizeof(int) * Bp, h->stream);
@@ -348,19 +350,27 @@ int ilqgb_upload(ilqgb_handle *h, const double *x0, const double *u_nom)
     if (ensure_stage(h, B * T * nu + B * nx)) return -1;
     if (ilqgk_h2d(h->d_stage, u_nom, sizeof(double) * B * T * nu, h->stream)) return failk(h);
     if (ilqgk_h2d(h->d_stage + B * T * nu, x0, sizeof(double) * B * nx, h->stream)) return failk(h);
-    if (ilqgk_launch_scatter(h->d_stage, h->w.U[0], h->B, h->Bp, h->T, h->d.nu, h->stream)) return failk(h);
+    /* controls into the u part of buffer 0's records; x0 into its own [NX][Bp] array */
+    if (ilqgk_launch_scatter(h->d_stage, h->w.XU[0], h->B, h->T, h->d.nu, (long long)h->Bp * h->d.rxu, h->d.rxu, 1, h->d.nx, h->stream)) return failk(h);
     h->n_launches += 2;
-    if (ilqgk_launch_scatter(h->d_stage + B * T * nu, h->w.x0, h->B, h->Bp, 1, h->d.nx, h->stream)) return failk(h);
+    if (ilqgk_launch_scatter(h->d_stage + B * T * nu, h->w.x0, h->B, 1, h->d.nx, 0, 1, h->Bp, 0, h->stream)) return failk(h);
     h->started = 0;
     return 0;
 }
 
-static int gather_to_host(ilqgb_handle *h, const double *src, const double *alt, const int *sel, int n_k, int n_i, double *out)
+typedef struct {
+    long long stride_k, stride_b, stride_i, off;
+} lay_t;
+
+static lay_t lay_rec(const ilqgb_handle *h, int rec, int off) { lay_t l = {(long long)h->Bp * rec, rec, 1, off}; return l; }
+static lay_t lay_soa(const ilqgb_handle *h, int n_i) { lay_t l = {(long long)h->Bp * n_i, 1, h->Bp, 0}; return l; }
+
+static int gather_to_host(ilqgb_handle *h, const double *src, const double *alt, const int *sel, int n_k, int n_i, lay_t L, double *out)
 {
     const size_t n = (size_t)h->B * n_k * n_i;
     if (!n) return 0;
     if (ensure_stage(h, n)) return -1;
-    if (ilqgk_launch_gather(src, alt, sel, h->d_stage, h->B, h->Bp, n_k, n_i, h->stream)) return failk(h);
+    if (ilqgk_launch_gather(src, alt, sel, h->d_stage, h->B, n_k, n_i, L.stride_k, L.stride_b, L.stride_i, L.off, h->stream)) return failk(h);
     h->n_launches++;
     if (ilqgk_d2h(out, h->d_stage, sizeof(double) * n, h->stream)) return failk(h);
     return 0;
@@ -372,11 +382,11 @@ int ilqgb_download(ilqgb_handle *h, double *x, double *u, double *cost, int *ite
     if (ilqgk_set_device(h->device)) return failk(h);
     /* the staging buffer is reused: serialise x and u through the stream (stream order keeps this correct) */
     if (x) {
-        if (gather_to_host(h, h->w.X[0], h->w.X[1], h->w.cur, h->T + 1, h->d.nx, x)) return -1;
+        if (gather_to_host(h, h->w.XU[0], h->w.XU[1], h->w.cur, h->T + 1, h->d.nx, lay_rec(h, h->d.rxu, 0), x)) return -1;
         if (ilqgk_stream_sync(h->stream)) return failk(h);
     }
     if (u) {
-        if (gather_to_host(h, h->w.U[0], h->w.U[1], h->w.cur, h->T, h->d.nu, u)) return -1;
+        if (gather_to_host(h, h->w.XU[0], h->w.XU[1], h->w.cur, h->T, h->d.nu, lay_rec(h, h->d.rxu, h->d.nx), u)) return -1;
         if (ilqgk_stream_sync(h->stream)) return failk(h);
     }
     if (cost && ilqgk_d2h(cost, h->w.cost, sizeof(double) * B, h->stream)) return failk(h);
@@ -466,7 +476,7 @@ static int launch_pass(ilqgb_handle *h, int do_derivs, int do_back, int do_ls)
     if (do_ls) {
         p = timing_begin(h, TC_LINESEARCH);
         if (ilqgk_launch_linesearch(&h->w, &h->o, h->params, h->iter, h->stream)) return failk(h);
-        h->n_launches++;
+        h->n_launches += h->o.n_alpha;
         timing_end(h, p);
         if (ilqgk_has_post()) {
             p = timing_begin(h, TC_POST);
@@ -568,19 +578,20 @@ long ilqgb_get(ilqgb_handle *h, const char *f, double *out)
         const double *src = NULL, *alt = NULL;
         const int *sel = NULL;
         int n_k = 0, n_i = 0;
-        if (!strcmp(f, "x")) { src = w->X[0]; alt = w->X[1]; sel = w->cur; n_k = h->T + 1; n_i = d->nx; }
-        else if (!strcmp(f, "u")) { src = w->U[0]; alt = w->U[1]; sel = w->cur; n_k = h->T; n_i = d->nu; }
-        else if (!strcmp(f, "l")) { src = w->l; n_k = h->T; n_i = d->nu; }
-        else if (!strcmp(f, "L")) { src = w->Lg; n_k = h->T; n_i = d->nu * d->nx; }
-        else if (!strcmp(f, "v1")) { src = w->V1; n_k = h->T; n_i = d->nv1; }
-        else if (!strcmp(f, "v2") && d->full_ddp) { src = w->V2; n_k = h->T; n_i = d->nv2; }
-        else if (!strcmp(f, "fd")) { src = w->FD; n_k = 1; n_i = d->nx + d->nqxx; }
-        else if (!strcmp(f, "mu_f")) { src = w->muF; n_k = 1; n_i = d->n_mu_f; }
-        else if (!strcmp(f, "mu_r")) { src = w->muR; n_k = h->T; n_i = d->n_mu_r; }
-        else if (!strcmp(f, "tr_lambda") && w->tr_lambda) { src = w->tr_lambda; n_k = h->trace_cap; n_i = 1; }
-        else if (!strcmp(f, "tr_newcost") && w->tr_newcost) { src = w->tr_newcost; n_k = h->trace_cap; n_i = 1; }
+        lay_t L;
+        if (!strcmp(f, "x")) { src = w->XU[0]; alt = w->XU[1]; sel = w->cur; n_k = h->T + 1; n_i = d->nx; L = lay_rec(h, d->rxu, 0); }
+        else if (!strcmp(f, "u")) { src = w->XU[0]; alt = w->XU[1]; sel = w->cur; n_k = h->T; n_i = d->nu; L = lay_rec(h, d->rxu, d->nx); }
+        else if (!strcmp(f, "l")) { src = w->LL; n_k = h->T; n_i = d->nu; L = lay_rec(h, d->rll, 0); }
+        else if (!strcmp(f, "L")) { src = w->LL; n_k = h->T; n_i = d->nu * d->nx; L = lay_rec(h, d->rll, d->nu); }
+        else if (!strcmp(f, "v1")) { src = w->V1; n_k = h->T; n_i = d->nv1; L = lay_soa(h, n_i); }
+        else if (!strcmp(f, "v2") && d->full_ddp) { src = w->V2; n_k = h->T; n_i = d->nv2; L = lay_soa(h, n_i); }
+        else if (!strcmp(f, "fd")) { src = w->FD; n_k = 1; n_i = d->nx + d->nqxx; L = lay_soa(h, n_i); }
+        else if (!strcmp(f, "mu_f")) { src = w->muF; n_k = 1; n_i = d->n_mu_f; L = lay_soa(h, n_i); }
+        else if (!strcmp(f, "mu_r")) { src = w->muR; n_k = h->T; n_i = d->n_mu_r; L = lay_soa(h, n_i); }
+        else if (!strcmp(f, "tr_lambda") && w->tr_lambda) { src = w->tr_lambda; n_k = h->trace_cap; n_i = 1; L = lay_soa(h, 1); }
+        else if (!strcmp(f, "tr_newcost") && w->tr_newcost) { src = w->tr_newcost; n_k = h->trace_cap; n_i = 1; L = lay_soa(h, 1); }
         else return fail(h, "unknown field");
-        if (gather_to_host(h, src, alt, sel, n_k, n_i, out)) return -1;
+        if (gather_to_host(h, src, alt, sel, n_k, n_i, L, out)) return -1;
         if (ilqgk_stream_sync(h->stream)) return failk(h);
         return (long)(B * n_k * n_i);
     }

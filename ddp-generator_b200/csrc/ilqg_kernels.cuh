@@ -16,7 +16,7 @@
  *   add_mul_vec / add_square_tri / add_mul2_tri   matMult.c:3-12 / 14-46 / 48-72
  *   box_qp (+ masked Cholesky / inverse)          boxQP.c:39-238, cholesky.c:6-27, 51-74
  *   k_backpass                                    back_pass.c:38-257 + iLQG.c:261-303 (lambda loop, gradient exit)
- *   k_rollout                                     iLQG_func.tem:121-185 (forward_pass), line_search.c:33-78,
+ *   k_ls_round, k_init                            iLQG_func.tem:121-185 (forward_pass), line_search.c:33-78,
  *                                                 iLQG.c:311-361 (accept / reject), iLQG_mex.c:108-120 (initial)
  *   k_derivs                                      iLQG_func.tem:187-221 (calc_derivs)
  *   k_post                                        iLQG_func.tem:417-509 (update_multipliers) + cost-only pass
@@ -32,6 +32,12 @@ namespace ilqg {
 constexpr int MAX_ALPHA = ILQG_MAX_ALPHA;
 constexpr int BP_BLOCK = 64;   /* threads per block for the sequential-in-time kernels */
 constexpr int DV_BLOCK = 128;  /* threads per block for the derivative kernel */
+#ifndef ILQG_BP_MINBLOCKS
+#define ILQG_BP_MINBLOCKS 1
+#endif
+#ifndef ILQG_LS_MINBLOCKS
+#define ILQG_LS_MINBLOCKS 1
+#endif
 
 enum { ST_RUNNING = 0, ST_DONE = 1 };
 enum { POST_NONE = 0, POST_MULT = 1, POST_COST = 2 };
@@ -299,6 +305,35 @@ __device__ __forceinline__ int box_qp(const double *H, const double *g, const do
     return 1;
 }
 
+/* ---- per-(step, problem) records in HBM ---------------------------------------------------------------------------
+ * The data a rollout reads and writes is stored as one small contiguous record per (timestep, problem):
+ *   XU[buf][k][b][RXU] = x (NX) | u (NU) | pad        LL[k][b][RLL] = l (NU) | L (NU*NX) | pad
+ * with record sizes rounded up to 32-byte sectors.  Any lane -> problem mapping (the line search works on compacted
+ * problem lists) then moves only fully used sectors, and a warp with lane == problem still reads one contiguous run. */
+template <class P> struct Rec {
+    static constexpr int RXU = ((P::NX + P::NU + 3) / 4) * 4;
+    static constexpr int RLL = ((P::NU + P::NU * P::NX + 3) / 4) * 4;
+};
+
+template <int N> __device__ __forceinline__ void ld_rec(const double *p, double *out)
+{
+    const double2 *p2 = reinterpret_cast<const double2 *>(p);
+#pragma unroll
+    for (int i = 0; i < (N + 1) / 2; i++) {
+        const double2 v = p2[i];
+        out[2 * i] = v.x;
+        if (2 * i + 1 < N) out[2 * i + 1] = v.y;
+    }
+}
+
+/* stores whole 16-byte pairs: `in` must hold N rounded up to even (pad with anything finite) */
+template <int N> __device__ __forceinline__ void st_rec(double *p, const double *in)
+{
+    double2 *p2 = reinterpret_cast<double2 *>(p);
+#pragma unroll
+    for (int i = 0; i < N / 2; i++) p2[i] = make_double2(in[2 * i], in[2 * i + 1]);
+}
+
 /* ---- per-step dense record the backward pass works on ------------------------------------------------------------- */
 template <class P> struct Dense {
     double fx[P::NX * P::NX], fu[P::NX * P::NU], cx[P::NX], cxx[P::NQXX], cu[P::NU], cuu[P::NQUU], cxu[P::NQXU];
@@ -337,15 +372,12 @@ __global__ void __launch_bounds__(DV_BLOCK) k_derivs(Work w, ParamBlock<P> pb)
     if (w.status[b] != ST_RUNNING || !w.new_deriv[b]) return;
     const size_t Bp = w.Bp;
     const int cur = w.cur[b];
-    double x[P::NX], u[P::NU], mu[P::N_MU_R + P::N_MU_F + 1];
-    const double *Xc = w.X[cur] + (size_t)k * P::NX * Bp + b;
-#pragma unroll
-    for (int i = 0; i < P::NX; i++) x[i] = Xc[i * Bp];
+    constexpr int RXU = Rec<P>::RXU;
+    double xu[RXU], mu[P::N_MU_R + P::N_MU_F + 1];
+    ld_rec<P::NX + P::NU>(w.XU[cur] + ((size_t)k * Bp + b) * RXU, xu);
+    const double *x = xu, *u = xu + P::NX;
     bool ok;
     if (k < w.T) {
-        const double *Uc = w.U[cur] + (size_t)k * P::NU * Bp + b;
-#pragma unroll
-        for (int i = 0; i < P::NU; i++) u[i] = Uc[i * Bp];
 #pragma unroll
         for (int i = 0; i < P::N_MU_R; i++) mu[i] = w.muR[((size_t)k * P::N_MU_R + i) * Bp + b];
         double v1[P::NV1], v2[P::NV2];
@@ -380,7 +412,7 @@ __global__ void __launch_bounds__(DV_BLOCK) k_derivs(Work w, ParamBlock<P> pb)
  * K2: backward pass, one lane per problem, incl. the regularisation retry loop and the gradient exit.
  * ===================================================================================================================== */
 template <class P, bool FULL>
-__global__ void __launch_bounds__(BP_BLOCK) k_backpass(Work w, Opts o, ParamBlock<P> pb, int iter)
+__global__ void __launch_bounds__(BP_BLOCK, ILQG_BP_MINBLOCKS) k_backpass(Work w, Opts o, ParamBlock<P> pb, int iter)
 {
     constexpr int NX = P::NX, NU = P::NU, NQXX = P::NQXX, NQUU = P::NQUU, NQXU = P::NQXU;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -533,12 +565,15 @@ __global__ void __launch_bounds__(BP_BLOCK) k_backpass(Work w, Opts o, ParamBloc
                 }
             }
             {
-                double *lo = w.l + (size_t)k * NU * Bp + b;
+                constexpr int RLL = Rec<P>::RLL;
+                double rec[RLL];
 #pragma unroll
-                for (int i = 0; i < NU; i++) lo[i * Bp] = lk[i];
-                double *Lo = w.Lg + (size_t)k * NU * NX * Bp + b;
+                for (int i = 0; i < NU; i++) rec[i] = lk[i];
 #pragma unroll
-                for (int i = 0; i < NU * NX; i++) Lo[i * Bp] = Lk[i];
+                for (int i = 0; i < NU * NX; i++) rec[NU + i] = Lk[i];
+#pragma unroll
+                for (int i = NU + NU * NX; i < RLL; i++) rec[i] = 0.0;
+                st_rec<RLL>(w.LL + ((size_t)k * Bp + b) * RLL, rec);
             }
             /* expected reduction (back_pass.c:204-214) */
 #pragma unroll
@@ -577,11 +612,12 @@ __global__ void __launch_bounds__(BP_BLOCK) k_backpass(Work w, Opts o, ParamBloc
                     }
             /* gradient measure (back_pass.c:244-251) */
             {
-                const double *Uc = w.U[cur] + (size_t)k * NU * Bp + b;
+                double xu[Rec<P>::RXU];
+                ld_rec<NX + NU>(w.XU[cur] + ((size_t)k * Bp + b) * Rec<P>::RXU, xu);
                 double gmax = 0.0;
 #pragma unroll
                 for (int i = 0; i < NU; i++) {
-                    const double gi = fabs(lk[i]) / (fabs(Uc[i * Bp]) + 1.0);
+                    const double gi = fabs(lk[i]) / (fabs(xu[NX + i]) + 1.0);
                     if (gi > gmax) gmax = gi;
                 }
                 g_sum += gmax;
@@ -622,49 +658,47 @@ template <class P>
 __device__ __forceinline__ bool rollout(const Work &w, const ParamBlock<P> &pb, int b, int from, int to, double alpha,
                                         double w_pen_l, double w_pen_f, double &csum)
 {
-    constexpr int NX = P::NX, NU = P::NU;
+    constexpr int NX = P::NX, NU = P::NU, RXU = Rec<P>::RXU, RLL = Rec<P>::RLL;
     const size_t Bp = w.Bp;
     const int T = w.T;
-    double x[NX], xn[NX], u[NU], mu[P::N_MU_R + P::N_MU_F + 1];
+    double xu[RXU], xn[NX], mu[P::N_MU_R + P::N_MU_F + 1];
+    double *x = xu, *u = xu + NX;
+#pragma unroll
+    for (int i = 0; i < RXU; i++) xu[i] = 0.0;
 #pragma unroll
     for (int i = 0; i < NX; i++) x[i] = w.x0[(size_t)i * Bp + b];
     csum = 0.0;
     for (int k = 0; k < T; k++) {
-        const double *Un = w.U[from] + (size_t)k * NU * Bp + b;
+        double nom[RXU];
+        ld_rec<NX + NU>(w.XU[from] + ((size_t)k * Bp + b) * RXU, nom);
         if (alpha != 0.0) {
-            const double *Xn = w.X[from] + (size_t)k * NX * Bp + b;
-            const double *ln = w.l + (size_t)k * NU * Bp + b;
-            const double *Ln = w.Lg + (size_t)k * NU * NX * Bp + b;
+            double ll[RLL];
+            ld_rec<NU + NU * NX>(w.LL + ((size_t)k * Bp + b) * RLL, ll);
 #pragma unroll
-            for (int j = 0; j < NU; j++) u[j] = Un[j * Bp] + ln[j * Bp] * alpha;
+            for (int j = 0; j < NU; j++) u[j] = nom[NX + j] + ll[j] * alpha;
 #pragma unroll
             for (int i = 0; i < NX; i++) {
-                const double dx = x[i] - Xn[i * Bp];
+                const double dx = x[i] - nom[i];
 #pragma unroll
-                for (int j = 0; j < NU; j++) u[j] += Ln[(j + i * NU) * Bp] * dx;
+                for (int j = 0; j < NU; j++) u[j] += ll[NU + j + i * NU] * dx;
             }
         } else {
 #pragma unroll
-            for (int j = 0; j < NU; j++) u[j] = Un[j * Bp];
+            for (int j = 0; j < NU; j++) u[j] = nom[NX + j];
         }
 #pragma unroll
         for (int i = 0; i < P::N_MU_R; i++) mu[i] = w.muR[((size_t)k * P::N_MU_R + i) * Bp + b];
         double c;
         const bool ok = P::step(x, u, pb.v, w.pk, k, T, w_pen_l, mu, xn, c);
-        double *Xo = w.X[to] + (size_t)k * NX * Bp + b;
-        double *Uo = w.U[to] + (size_t)k * NU * Bp + b;
-#pragma unroll
-        for (int i = 0; i < NX; i++) Xo[i * Bp] = x[i];
-#pragma unroll
-        for (int j = 0; j < NU; j++) Uo[j * Bp] = u[j];
+        st_rec<RXU>(w.XU[to] + ((size_t)k * Bp + b) * RXU, xu);
         if (!ok) return false;
         csum += c;
 #pragma unroll
         for (int i = 0; i < NX; i++) x[i] = xn[i];
     }
-    double *Xo = w.X[to] + (size_t)T * NX * Bp + b;
 #pragma unroll
-    for (int i = 0; i < NX; i++) Xo[i * Bp] = x[i];
+    for (int j = 0; j < NU; j++) u[j] = 0.0;
+    st_rec<RXU>(w.XU[to] + ((size_t)T * Bp + b) * RXU, xu);
 #pragma unroll
     for (int i = 0; i < P::N_MU_F; i++) mu[i] = w.muF[(size_t)i * Bp + b];
     double c;
@@ -678,31 +712,24 @@ template <class P>
 __device__ __forceinline__ bool cost_pass(const Work &w, const ParamBlock<P> &pb, int b, int buf, double w_pen_l,
                                           double w_pen_f, double &csum)
 {
-    constexpr int NX = P::NX, NU = P::NU;
+    constexpr int NX = P::NX, NU = P::NU, RXU = Rec<P>::RXU;
     const size_t Bp = w.Bp;
     const int T = w.T;
-    double x[NX], u[NU], mu[P::N_MU_R + P::N_MU_F + 1];
+    double xu[RXU], mu[P::N_MU_R + P::N_MU_F + 1];
     csum = 0.0;
     for (int k = 0; k < T; k++) {
-        const double *Xn = w.X[buf] + (size_t)k * NX * Bp + b;
-        const double *Un = w.U[buf] + (size_t)k * NU * Bp + b;
-#pragma unroll
-        for (int i = 0; i < NX; i++) x[i] = Xn[i * Bp];
-#pragma unroll
-        for (int j = 0; j < NU; j++) u[j] = Un[j * Bp];
+        ld_rec<NX + NU>(w.XU[buf] + ((size_t)k * Bp + b) * RXU, xu);
 #pragma unroll
         for (int i = 0; i < P::N_MU_R; i++) mu[i] = w.muR[((size_t)k * P::N_MU_R + i) * Bp + b];
         double c;
-        if (!P::step_cost(x, u, pb.v, w.pk, k, T, w_pen_l, mu, c)) return false;
+        if (!P::step_cost(xu, xu + NX, pb.v, w.pk, k, T, w_pen_l, mu, c)) return false;
         csum += c;
     }
-    const double *Xn = w.X[buf] + (size_t)T * NX * Bp + b;
-#pragma unroll
-    for (int i = 0; i < NX; i++) x[i] = Xn[i * Bp];
+    ld_rec<NX>(w.XU[buf] + ((size_t)T * Bp + b) * RXU, xu);
 #pragma unroll
     for (int i = 0; i < P::N_MU_F; i++) mu[i] = w.muF[(size_t)i * Bp + b];
     double c;
-    if (!P::final_cost(x, pb.v, w.pk, T, T, w_pen_f, mu, c)) return false;
+    if (!P::final_cost(xu, pb.v, w.pk, T, T, w_pen_f, mu, c)) return false;
     csum += c;
     return true;
 }
@@ -761,10 +788,12 @@ __global__ void __launch_bounds__(BP_BLOCK) k_init(Work w, Opts o, ParamBlock<P>
         double x[P::NX], u[P::NU], mu[P::N_MU_R + P::N_MU_F + 1], hval[P::N_MU_R + P::N_MU_F + 1],
             mun[P::N_MU_R + P::N_MU_F + 1];
         if (P::N_MU_R > 0 && T > 0) {
+            double xu[Rec<P>::RXU];
+            ld_rec<P::NX + P::NU>(w.XU[1] + (size_t)b * Rec<P>::RXU, xu);
 #pragma unroll
-            for (int i = 0; i < P::NX; i++) x[i] = w.X[1][(size_t)i * Bp + b];
+            for (int i = 0; i < P::NX; i++) x[i] = xu[i];
 #pragma unroll
-            for (int i = 0; i < P::NU; i++) u[i] = w.U[1][(size_t)i * Bp + b];
+            for (int i = 0; i < P::NU; i++) u[i] = xu[P::NX + i];
 #pragma unroll
             for (int i = 0; i < P::N_MU_R; i++) mu[i] = w.muR[(size_t)i * Bp + b];
             P::mult_running(x, u, pb.v, w.pk, 0, T, o.w_pen_init_l, mu, hval, mun);
@@ -772,8 +801,7 @@ __global__ void __launch_bounds__(BP_BLOCK) k_init(Work w, Opts o, ParamBlock<P>
             for (int i = 0; i < P::N_MU_R; i++) w.lastR[(size_t)i * Bp + b] = hval[i];
         }
         if (P::N_MU_F > 0) {
-#pragma unroll
-            for (int i = 0; i < P::NX; i++) x[i] = w.X[1][((size_t)T * P::NX + i) * Bp + b];
+            ld_rec<P::NX>(w.XU[1] + ((size_t)T * Bp + b) * Rec<P>::RXU, x);
 #pragma unroll
             for (int i = 0; i < P::N_MU_F; i++) mu[i] = w.muF[(size_t)i * Bp + b];
             P::mult_final(x, pb.v, w.pk, T, T, o.w_pen_init_f, mu, hval, mun);
@@ -783,71 +811,99 @@ __global__ void __launch_bounds__(BP_BLOCK) k_init(Work w, Opts o, ParamBlock<P>
     }
 }
 
+/* K3: line search, one ROUND per launch.  Round r rolls out alpha[r] for every problem that has not accepted a step
+ * yet (line_search.c:37-60 tries the alphas in order and takes the first with z > zMin).  Round 0 runs over all
+ * running problems with lane == problem; every later round runs over the compacted list of problems the previous
+ * round left undecided, so all lanes of a warp do the same amount of work (one full rollout) instead of idling
+ * while one neighbour backtracks.  The list keeps the problems of a block in order, which keeps most 32-byte
+ * sectors shared between neighbouring lanes.  The problem that accepts, or exhausts the alphas, runs the
+ * accept/reject bookkeeping of iLQG.c:311-361 in the same thread. */
 template <class P>
-__global__ void __launch_bounds__(BP_BLOCK) k_linesearch(Work w, Opts o, ParamBlock<P> pb, int iter)
+__global__ void __launch_bounds__(BP_BLOCK, ILQG_LS_MINBLOCKS)
+k_ls_round(Work w, Opts o, ParamBlock<P> pb, int iter, int round)
 {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= w.B) return;
-    if (w.status[b] != ST_RUNNING) return;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const size_t Bp = w.Bp;
-    const int cur = w.cur[b];
-    const double cost = w.cost[b], dV0 = w.dV0[b], dV1 = w.dV1[b];
-    double w_pen_l = w.w_pen_l[b], w_pen_f = w.w_pen_f[b];
-    double lambda = w.lambda[b], dlambda = w.dlambda[b];
-    double cnew = w.new_cost[b], dcost = w.dcost[b], expected = w.expected[b];
-    if (w.tr_lambda) w.tr_lambda[(size_t)iter * Bp + b] = lambda;
-    w.n_ls[b] += 1;
-
-    int tried = 0;
-    bool accepted = false;
-    for (tried = 0; tried < o.n_alpha; tried++) {
-        const double alpha = o.alpha[tried];
-        double csum;
-        if (!rollout<P>(w, pb, b, cur, cur ^ 1, alpha, w_pen_l, w_pen_f, csum)) {
-            cnew = csum;
-            continue;
+    int b = -1;
+    if (round == 0) {
+        if (tid < w.B && w.status[tid] == ST_RUNNING) b = tid;
+    } else {
+        if (tid < w.ls_count[round]) b = w.ls_list[round & 1][tid];
+    }
+    bool undecided = false;
+    if (b >= 0) {
+        const int cur = w.cur[b];
+        const double cost = w.cost[b], dV0 = w.dV0[b], dV1 = w.dV1[b];
+        double w_pen_l = w.w_pen_l[b], w_pen_f = w.w_pen_f[b];
+        double cnew, dcost = w.dcost[b], expected = w.expected[b];
+        if (round == 0) {
+            if (w.tr_lambda) w.tr_lambda[(size_t)iter * Bp + b] = w.lambda[b];
+            w.n_ls[b] += 1;
         }
-        cnew = csum;
-        dcost = cost - cnew;
-        expected = -alpha * (dV0 + alpha * dV1);
-        const double z = (expected > 0) ? dcost / expected : 0.0;
-        if (z > o.zMin) {
-            accepted = true;
-            break;
+        w.n_roll[b] += 1;
+        const double alpha = o.alpha[round];
+        bool accepted = false;
+        const bool ok = rollout<P>(w, pb, b, cur, cur ^ 1, alpha, w_pen_l, w_pen_f, cnew);
+        if (ok) {
+            dcost = cost - cnew;
+            expected = -alpha * (dV0 + alpha * dV1);
+            const double z = (expected > 0) ? dcost / expected : 0.0;
+            accepted = z > o.zMin;
+        }
+        w.new_cost[b] = cnew;
+        w.dcost[b] = dcost;
+        w.expected[b] = expected;
+        if (accepted || round == o.n_alpha - 1) {
+            double lambda = w.lambda[b], dlambda = w.dlambda[b];
+            if (w.tr_alpha) w.tr_alpha[(size_t)iter * Bp + b] = accepted ? round + 1 : o.n_alpha + 1;
+            if (w.tr_newcost) w.tr_newcost[(size_t)iter * Bp + b] = cnew;
+            int post = POST_NONE;
+            if (accepted) { /* iLQG.c:311-338 */
+                lower_lambda(o, lambda, dlambda);
+                w.cur[b] = cur ^ 1;
+                w.cost[b] = cnew;
+                w.new_deriv[b] = 1;
+                if (dcost < o.tolFun)
+                    finish(w, b, iter, 1);
+                else
+                    post = POST_MULT;
+            } else { /* iLQG.c:340-361 */
+                raise_lambda(o, lambda, dlambda);
+                if (o.w_pen_fact2 > 1.0) {
+                    w.w_pen_l[b] = dmin(o.w_pen_max_l, w_pen_l * o.w_pen_fact2);
+                    w.w_pen_f[b] = dmin(o.w_pen_max_f, w_pen_f * o.w_pen_fact2);
+                    post = POST_COST;
+                }
+                if (lambda > o.lambdaMax)
+                    finish(w, b, iter, 1); /* backPassDone is set and iter < max_iter: the reference returns 1 here */
+            }
+            w.post_mode[b] = post;
+            w.lambda[b] = lambda;
+            w.dlambda[b] = dlambda;
+        } else {
+            undecided = true;
         }
     }
-    w.n_roll[b] += (tried < o.n_alpha) ? tried + 1 : o.n_alpha;
-    if (w.tr_alpha) w.tr_alpha[(size_t)iter * Bp + b] = tried + 1;
-    if (w.tr_newcost) w.tr_newcost[(size_t)iter * Bp + b] = cnew;
-    w.new_cost[b] = cnew;
-    w.dcost[b] = dcost;
-    w.expected[b] = expected;
-
-    int post = POST_NONE;
-    if (accepted) { /* iLQG.c:311-338 */
-        lower_lambda(o, lambda, dlambda);
-        w.cur[b] = cur ^ 1;
-        w.cost[b] = cnew;
-        w.new_deriv[b] = 1;
-        if (dcost < o.tolFun)
-            finish(w, b, iter, 1);
-        else
-            post = POST_MULT;
-    } else { /* iLQG.c:340-361 */
-        raise_lambda(o, lambda, dlambda);
-        if (o.w_pen_fact2 > 1.0) {
-            w_pen_l = dmin(o.w_pen_max_l, w_pen_l * o.w_pen_fact2);
-            w_pen_f = dmin(o.w_pen_max_f, w_pen_f * o.w_pen_fact2);
-            w.w_pen_l[b] = w_pen_l;
-            w.w_pen_f[b] = w_pen_f;
-            post = POST_COST;
+    /* ordered compaction of the undecided problems of this block into the next round's list */
+    __shared__ int s_warp[BP_BLOCK / 32];
+    __shared__ int s_base;
+    const unsigned ballot = __ballot_sync(0xffffffffu, undecided);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) s_warp[wid] = __popc(ballot);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int i = 0; i < BP_BLOCK / 32; i++) {
+            const int c = s_warp[i];
+            s_warp[i] = tot;
+            tot += c;
         }
-        if (lambda > o.lambdaMax)
-            finish(w, b, iter, 1); /* backPassDone is set and iter < max_iter: the reference returns 1 here */
+        s_base = tot ? atomicAdd(&w.ls_count[round + 1], tot) : 0;
     }
-    w.post_mode[b] = post;
-    w.lambda[b] = lambda;
-    w.dlambda[b] = dlambda;
+    __syncthreads();
+    if (undecided)
+        w.ls_list[(round + 1) & 1][s_base + s_warp[wid] + __popc(ballot & ((1u << lane) - 1u))] = b;
 }
 
 /* K5: update_multipliers(o, 0) and the cost-only pass that follows an accepted step, or the cost-only pass after a
@@ -870,12 +926,12 @@ __global__ void __launch_bounds__(BP_BLOCK) k_post(Work w, Opts o, ParamBlock<P>
         if (NR > 0) {
             bool increase = false;
             for (int k = 0; k < T; k++) {
-                const double *Xn = w.X[cur] + (size_t)k * NX * Bp + b;
-                const double *Un = w.U[cur] + (size_t)k * NU * Bp + b;
+                double xu[Rec<P>::RXU];
+                ld_rec<NX + NU>(w.XU[cur] + ((size_t)k * Bp + b) * Rec<P>::RXU, xu);
 #pragma unroll
-                for (int i = 0; i < NX; i++) x[i] = Xn[i * Bp];
+                for (int i = 0; i < NX; i++) x[i] = xu[i];
 #pragma unroll
-                for (int j = 0; j < NU; j++) u[j] = Un[j * Bp];
+                for (int j = 0; j < NU; j++) u[j] = xu[NX + j];
 #pragma unroll
                 for (int i = 0; i < NR; i++) mu[i] = w.muR[((size_t)k * NR + i) * Bp + b];
                 P::mult_running(x, u, pb.v, w.pk, k, T, w_pen_l, mu, hval, mun);
@@ -895,9 +951,7 @@ __global__ void __launch_bounds__(BP_BLOCK) k_post(Work w, Opts o, ParamBlock<P>
         }
         if (NF > 0) {
             bool increase = false;
-            const double *Xn = w.X[cur] + (size_t)T * NX * Bp + b;
-#pragma unroll
-            for (int i = 0; i < NX; i++) x[i] = Xn[i * Bp];
+            ld_rec<NX>(w.XU[cur] + ((size_t)T * Bp + b) * Rec<P>::RXU, x);
 #pragma unroll
             for (int i = 0; i < NF; i++) mu[i] = w.muF[(size_t)i * Bp + b];
             P::mult_final(x, pb.v, w.pk, T, T, w_pen_f, mu, hval, mun);
@@ -942,26 +996,30 @@ __global__ void k_count_active(Work w, int *out)
     if (threadIdx.x == 0 && a) atomicAdd(out, a);
 }
 
-/* layout changes between the caller's problem-major arrays and the device's [k][i][b] arrays */
-__global__ void k_scatter(const double *src /*[B][n_k][n_i]*/, double *dst /*[n_k][n_i][Bp]*/, int B, int Bp, int n_k, int n_i)
+/* layout changes between the caller's problem-major arrays [B][n_k][n_i] and device arrays addressed as
+ * base[(k * stride_k + b) * stride_b + off + i * stride_i]  (records: stride_k = Bp, stride_b = record size, stride_i = 1;
+ * structure-of-arrays [k][i][Bp]: handled by the caller passing stride_b = 1, stride_i = Bp, stride_k = n_i * Bp / 1) */
+struct Layout {
+    long long stride_k, stride_b, stride_i, off;
+};
+
+__global__ void k_scatter(const double *src, double *dst, int B, int n_k, int n_i, Layout L)
 {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t per = (size_t)n_k * n_i;
     if (e >= per * B) return;
-    /* thread order follows dst (b fastest) so the stores coalesce; loads go through L2 */
-    const size_t b = e % B, ki = e / B;
-    dst[ki * Bp + b] = src[b * per + ki];
+    const size_t i = e % n_i, b = (e / n_i) % B, k = e / ((size_t)n_i * B);
+    dst[k * L.stride_k + b * L.stride_b + i * L.stride_i + L.off] = src[b * per + k * n_i + i];
 }
 
-__global__ void k_gather(const double *src /*[n_k][n_i][Bp]*/, double *dst /*[B][n_k][n_i]*/, const int *sel /* per-b buffer select or null */,
-                         const double *src_alt, int B, int Bp, int n_k, int n_i)
+__global__ void k_gather(const double *src, const double *src_alt, const int *sel, double *dst, int B, int n_k, int n_i, Layout L)
 {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t per = (size_t)n_k * n_i;
     if (e >= per * B) return;
-    const size_t b = e % B, ki = e / B;
+    const size_t i = e % n_i, b = (e / n_i) % B, k = e / ((size_t)n_i * B);
     const double *s = (sel && sel[b]) ? src_alt : src;
-    dst[b * per + ki] = s[ki * Bp + b];
+    dst[b * per + k * n_i + i] = s[k * L.stride_k + b * L.stride_b + i * L.stride_i + L.off];
 }
 
 } /* namespace ilqg */

@@ -18,14 +18,15 @@ typedef struct ilqg_opts {
 /* device workspace of one batch; all arrays are [..][Bp] with the problem index fastest */
 typedef struct ilqg_work {
     int B, Bp, T;
-    double *X[2], *U[2];       /* two trajectory buffers: x [T+1][NX][Bp], u [T][NU][Bp]; cur[b] says which is nominal */
+    double *XU[2];             /* two trajectory buffers of records [T+1][Bp][RXU] = x|u|pad; cur[b] says which is nominal */
     double *x0;                /* [NX][Bp] */
-    double *l, *Lg;            /* open-loop term [T][NU][Bp], feedback gains [T][NU*NX][Bp] */
+    double *LL;                /* control-law records [T][Bp][RLL] = l | L | pad (open-loop term, feedback gains) */
     double *V1, *V2, *FD;      /* time-varying derivative entries [T][NV1][Bp], [T][NV2][Bp]; final cx,cxx [NX+NQXX][Bp] */
     double *muR, *lastR, *muF, *lastF;
     const double *const *pk;   /* [k]-indexed parameters (device pointers), or null */
     double *cost, *new_cost, *dcost, *expected, *lambda, *dlambda, *g_norm, *dV0, *dV1, *w_pen_l, *w_pen_f;
     int *cur, *status, *new_deriv, *deriv_fail, *iterations, *result, *n_ls, *n_bp, *bp_done, *post_mode;
+    int *ls_list[2], *ls_count; /* line search: compacted lists of undecided problems (ping-pong), per-round counts */
     int *n_dv, *n_roll;        /* work counters: derivative sweeps consumed, rollouts tried (bench roofline accounting) */
     /* optional traces for parity tests (null when disabled) */
     double *tr_lambda, *tr_newcost; /* [max_iter][Bp] */
