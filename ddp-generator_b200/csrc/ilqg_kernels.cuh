@@ -33,7 +33,7 @@ constexpr int MAX_ALPHA = ILQG_MAX_ALPHA;
 constexpr int BP_BLOCK = 64;   /* threads per block for the sequential-in-time kernels */
 constexpr int DV_BLOCK = 128;  /* threads per block for the derivative kernel */
 #ifndef ILQG_BP_MINBLOCKS
-#define ILQG_BP_MINBLOCKS 1
+#define ILQG_BP_MINBLOCKS 8   /* 128 registers/thread: 16 warps per SM; measured faster than 212 registers at 8 warps */
 #endif
 #ifndef ILQG_LS_MINBLOCKS
 #define ILQG_LS_MINBLOCKS 1
@@ -334,6 +334,15 @@ template <int N> __device__ __forceinline__ void st_rec(double *p, const double 
     for (int i = 0; i < N / 2; i++) p2[i] = make_double2(in[2 * i], in[2 * i + 1]);
 }
 
+/* ---- asynchronous global->shared copies (LDGSTS) for software pipelining --------------------------------------------- */
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 /* ---- per-step dense record the backward pass works on ------------------------------------------------------------- */
 template <class P> struct Dense {
     double fx[P::NX * P::NX], fu[P::NX * P::NU], cx[P::NX], cxx[P::NQXX], cu[P::NU], cuu[P::NQUU], cxu[P::NQXU];
@@ -411,10 +420,36 @@ __global__ void __launch_bounds__(DV_BLOCK) k_derivs(Work w, ParamBlock<P> pb)
 /* =====================================================================================================================
  * K2: backward pass, one lane per problem, incl. the regularisation retry loop and the gradient exit.
  * ===================================================================================================================== */
+/* doubles per (step, problem) the backward pass consumes: time-varying derivative entries, the nominal control
+   (gradient measure), and the second-order entries when FULL_DDP */
+template <class P, bool FULL> __host__ __device__ constexpr int bp_fields() { return P::NV1 + P::NU + (FULL ? P::NV2_USED : 0); }
+
+template <class P, bool FULL>
+__device__ __forceinline__ void bp_issue(const Work &w, double *sm, int k, int stage, int b, int cur)
+{
+    constexpr int NF = bp_fields<P, FULL>();
+    const size_t Bp = w.Bp;
+    double *dst = sm + (size_t)stage * NF * BP_BLOCK + threadIdx.x;
+    const double *v1 = w.V1 + (size_t)k * P::NV1 * Bp + b;
+#pragma unroll
+    for (int i = 0; i < P::NV1; i++) cp_async8(dst + i * BP_BLOCK, v1 + i * Bp);
+    const double *un = w.XU[cur] + ((size_t)k * Bp + b) * Rec<P>::RXU + P::NX;
+#pragma unroll
+    for (int i = 0; i < P::NU; i++) cp_async8(dst + (P::NV1 + i) * BP_BLOCK, un + i);
+    if (FULL) {
+        const double *v2 = w.V2 + (size_t)k * P::NV2 * Bp + b;
+#pragma unroll
+        for (int i = 0; i < P::NV2_USED; i++) cp_async8(dst + (P::NV1 + P::NU + i) * BP_BLOCK, v2 + i * Bp);
+    }
+    cp_async_commit();
+}
+
 template <class P, bool FULL>
 __global__ void __launch_bounds__(BP_BLOCK, ILQG_BP_MINBLOCKS) k_backpass(Work w, Opts o, ParamBlock<P> pb, int iter)
 {
     constexpr int NX = P::NX, NU = P::NU, NQXX = P::NQXX, NQUU = P::NQUU, NQXU = P::NQXU;
+    constexpr int NF = bp_fields<P, FULL>();
+    __shared__ double sm[2 * NF * BP_BLOCK];
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= w.B) return;
     if (w.status[b] != ST_RUNNING) return;
@@ -451,12 +486,20 @@ __global__ void __launch_bounds__(BP_BLOCK, ILQG_BP_MINBLOCKS) k_backpass(Work w
         for (int i = 0; i < NU; i++) lk[i] = 0.0;
         bool failed = false;
 
+        /* two-stage LDGSTS pipeline: the inputs of step k-1 stream into shared memory while step k is computed.
+           Each thread copies and later reads only its own column, so no block barrier is needed. */
+        cp_async_wait<0>();
+        bp_issue<P, FULL>(w, sm, T - 1, 0, b, cur);
         for (int k = T - 1; k >= 0; k--) {
+            const int stage = (T - 1 - k) & 1;
+            if (k > 0) bp_issue<P, FULL>(w, sm, k - 1, stage ^ 1, b, cur);
+            else cp_async_commit();
+            cp_async_wait<1>();
+            const double *st = sm + (size_t)stage * NF * BP_BLOCK + threadIdx.x;
             {
                 double v1[P::NV1];
-                const double *i1 = w.V1 + (size_t)k * P::NV1 * Bp + b;
 #pragma unroll
-                for (int i = 0; i < P::NV1; i++) v1[i] = i1[i * Bp];
+                for (int i = 0; i < P::NV1; i++) v1[i] = st[i * BP_BLOCK];
                 P::unpack(v1, D);
             }
             double Qx[NX], Qu[NU], Qxx[NQXX], Quu[NQUU], Qxu[NQXU], QuuF[NQUU], Qxu_reg[NQXU];
@@ -478,9 +521,8 @@ __global__ void __launch_bounds__(BP_BLOCK, ILQG_BP_MINBLOCKS) k_backpass(Work w
             add_square_tri<NX, NX>(Qxx, Vxx, D.fx);
             if (FULL) {
                 double v2[P::NV2];
-                const double *i2 = w.V2 + (size_t)k * P::NV2 * Bp + b;
 #pragma unroll
-                for (int i = 0; i < P::NV2_USED; i++) v2[i] = i2[i * Bp];
+                for (int i = 0; i < P::NV2_USED; i++) v2[i] = st[(P::NV1 + NU + i) * BP_BLOCK];
                 P::add2_Qxu(Vx, v2, pb.v, Qxu);
                 P::add2_Quu(Vx, v2, pb.v, Quu);
                 P::add2_Qxx(Vx, v2, pb.v, Qxx);
@@ -612,12 +654,10 @@ __global__ void __launch_bounds__(BP_BLOCK, ILQG_BP_MINBLOCKS) k_backpass(Work w
                     }
             /* gradient measure (back_pass.c:244-251) */
             {
-                double xu[Rec<P>::RXU];
-                ld_rec<NX + NU>(w.XU[cur] + ((size_t)k * Bp + b) * Rec<P>::RXU, xu);
                 double gmax = 0.0;
 #pragma unroll
                 for (int i = 0; i < NU; i++) {
-                    const double gi = fabs(lk[i]) / (fabs(xu[NX + i]) + 1.0);
+                    const double gi = fabs(lk[i]) / (fabs(st[(P::NV1 + i) * BP_BLOCK]) + 1.0);
                     if (gi > gmax) gmax = gi;
                 }
                 g_sum += gmax;
@@ -669,11 +709,10 @@ __device__ __forceinline__ bool rollout(const Work &w, const ParamBlock<P> &pb, 
     for (int i = 0; i < NX; i++) x[i] = w.x0[(size_t)i * Bp + b];
     csum = 0.0;
     for (int k = 0; k < T; k++) {
-        double nom[RXU];
+        double nom[RXU], ll[RLL];
         ld_rec<NX + NU>(w.XU[from] + ((size_t)k * Bp + b) * RXU, nom);
+        if (alpha != 0.0) ld_rec<NU + NU * NX>(w.LL + ((size_t)k * Bp + b) * RLL, ll);
         if (alpha != 0.0) {
-            double ll[RLL];
-            ld_rec<NU + NU * NX>(w.LL + ((size_t)k * Bp + b) * RLL, ll);
 #pragma unroll
             for (int j = 0; j < NU; j++) u[j] = nom[NX + j] + ll[j] * alpha;
 #pragma unroll
