@@ -216,9 +216,9 @@ def main():
         return float(t.item())
 
     # ---- shard and inputs (pinned host memory) ---------------------------------------------------------------------
-    per = args.batch // world
-    first = rank * per
-    count = per if rank < world - 1 else args.batch - first
+    from ilqg_b200.sharding import shard_range
+
+    first, count = shard_range(args.batch, rank, world)
     nx, nu = 4, 2
     x0_t = torch.empty((count, nx), dtype=torch.float64).pin_memory()
     u0_t = torch.empty((count, T_HOR, nu), dtype=torch.float64).pin_memory()

@@ -223,9 +223,46 @@ DM_HD double dm_asin(double x)
 
 DM_HD double dm_acos(double x)
 {
-    /* acos = pi/2 - asin with the pi/2 tail folded in; adequate (<2 ulp) and deterministic */
-    const double pio2_hi = 1.57079632679489655800e+00, pio2_lo = 6.12323399573676603587e-17;
-    return pio2_hi - (dm_asin(x) - pio2_lo);
+    const double pi = 3.14159265358979311600e+00, pio2_hi = 1.57079632679489655800e+00, pio2_lo = 6.12323399573676603587e-17;
+    const double pS0 = 1.66666666666666657415e-01, pS1 = -3.25565818622400915405e-01,
+                 pS2 = 2.01212532134862925881e-01, pS3 = -4.00555345006794114027e-02,
+                 pS4 = 7.91534994289814532176e-04, pS5 = 3.47933107596021167570e-05;
+    const double qS1 = -2.40339491173441421878e+00, qS2 = 2.02094576023350569471e+00,
+                 qS3 = -6.88283971605453293030e-01, qS4 = 7.70381505559019352791e-02;
+    uint32_t ix = dm_hi_abs(x);
+    int neg = ((int64_t)dm_to_bits(x) < 0);
+    double z, p, q, r, s, w;
+    if (ix >= 0x3ff00000u) {
+        if (x == 1.0) return 0.0;
+        if (x == -1.0) return pi + 2.0 * pio2_lo;
+        return dm_nan();
+    }
+    if (ix < 0x3fe00000u) { /* |x| < 0.5 */
+        if (ix <= 0x3c600000u) return pio2_hi + pio2_lo;
+        z = x * x;
+        p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+        q = 1.0 + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+        r = p / q;
+        return pio2_hi - (x - (pio2_lo - x * r));
+    }
+    if (neg) { /* x < -0.5 */
+        z = (1.0 + x) * 0.5;
+        p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+        q = 1.0 + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+        s = dm_sqrt(z);
+        r = p / q;
+        w = r * s - pio2_lo;
+        return pi - 2.0 * (s + w);
+    }
+    z = (1.0 - x) * 0.5; /* x > 0.5 */
+    s = dm_sqrt(z);
+    double df = dm_from_bits(dm_to_bits(s) & 0xffffffff00000000ull);
+    double c = (z - df * df) / (s + df);
+    p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+    q = 1.0 + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+    r = p / q;
+    w = r * s + c;
+    return 2.0 * (df + w);
 }
 
 DM_HD double dm_fabs(double v) { return dm_from_bits(dm_to_bits(v) & 0x7fffffffffffffffull); }

@@ -145,7 +145,8 @@ static const char *rule_message(vrule r, double v)
     return NULL;
 }
 
-const char *ilqgb_set_opt(ilqgb_handle *h, const char *name, const double *value, int n)
+/* validation only (no handle, no device): NULL = acceptable, otherwise the reference's message */
+const char *ilqgb_validate_opt(const char *name, const double *value, int n)
 {
     size_t i;
     if (strcmp(name, "alpha") == 0) {
@@ -155,8 +156,6 @@ const char *ilqgb_set_opt(ilqgb_handle *h, const char *name, const double *value
             if (k > 0 && value[k] >= value[k - 1]) return "all alpha must be monotonically decreasing";
         }
         if (n > ILQG_MAX_ALPHA) return "at most 16 alpha values are supported";
-        memcpy(h->o.alpha, value, sizeof(double) * n);
-        h->o.n_alpha = n;
         return NULL;
     }
     if (strcmp(name, "debug_level") == 0) { /* accepted and validated; the batched solver prints nothing */
@@ -164,18 +163,33 @@ const char *ilqgb_set_opt(ilqgb_handle *h, const char *name, const double *value
         return rule_message(V_DEBUG, value[0]);
     }
     for (i = 0; i < sizeof k_opts / sizeof k_opts[0]; i++) {
-        const opt_desc *d = &k_opts[i];
-        const char *msg;
-        if (strcmp(name, d->name) != 0) continue;
+        if (strcmp(name, k_opts[i].name) != 0) continue;
         if (n != 1) return "parameter must be scalar";
-        if ((msg = rule_message(d->rule, value[0])) != NULL) return msg;
+        return rule_message(k_opts[i].rule, value[0]);
+    }
+    return "no such parameter";
+}
+
+const char *ilqgb_set_opt(ilqgb_handle *h, const char *name, const double *value, int n)
+{
+    size_t i;
+    const char *msg = ilqgb_validate_opt(name, value, n);
+    if (msg) return msg;
+    if (strcmp(name, "alpha") == 0) {
+        memcpy(h->o.alpha, value, sizeof(double) * n);
+        h->o.n_alpha = n;
+        return NULL;
+    }
+    for (i = 0; i < sizeof k_opts / sizeof k_opts[0]; i++) {
+        const opt_desc *d = &k_opts[i];
+        if (strcmp(name, d->name) != 0) continue;
         if (d->is_int)
             *(int *)((char *)&h->o + d->offset) = (int)value[0];
         else
             *(double *)((char *)&h->o + d->offset) = value[0];
         return NULL;
     }
-    return "no such parameter";
+    return NULL; /* debug_level */
 }
 
 int ilqgb_set_param(ilqgb_handle *h, int index, const double *value, int n)
@@ -246,7 +260,7 @@ ilqgb_handle *ilqgb_create(int device, int batch, int n_hor, int flags, void *st
             ilqgk_memset(w->XU[i], 0, sizeof(double) * (T + 1) * Bp * d->rxu, h->stream);
         }
         DALLOC(w->x0, double, d->nx * Bp);
-        DALLOC(w->LL, double, T * Bp * d->rll);
+        for (i = 0; i < 2; i++) DALLOC(w->LL[i], double, T * Bp * d->rll);
         DALLOC(w->V1, double, T * d->nv1 * Bp);
         DALLOC(w->V2, double, d->full_ddp ? T * d->nv2 * Bp : 1);
         DALLOC(w->FD, double, (d->nx + d->nqxx) * Bp);
@@ -332,13 +346,14 @@ static int ensure_stage(ilqgb_handle *h, size_t doubles)
 static int ensure_traces(ilqgb_handle *h)
 {
     size_t n;
-    if (!(h->flags & ILQGB_TRACE) || h->o.max_iter <= h->trace_cap) return 0;
-    n = (size_t)h->o.max_iter * h->Bp;
+    const int need = h->o.max_iter > 0 ? h->o.max_iter : 1;
+    if (!(h->flags & ILQGB_TRACE) || need <= h->trace_cap) return 0;
+    n = (size_t)need * h->Bp;
     h->w.tr_lambda = (double *)dalloc(h, sizeof(double) * n);
     h->w.tr_newcost = (double *)dalloc(h, sizeof(double) * n);
     h->w.tr_alpha = (int *)dalloc(h, sizeof(int) * n);
     if (!h->w.tr_lambda || !h->w.tr_newcost || !h->w.tr_alpha) return -1;
-    h->trace_cap = h->o.max_iter;
+    h->trace_cap = need;
     return 0;
 }
 
@@ -451,6 +466,11 @@ int ilqgb_start(ilqgb_handle *h)
 {
     if (ilqgk_set_device(h->device)) return failk(h);
     if (ensure_traces(h)) return -1;
+    if (h->flags & ILQGB_TRACE) { /* parity mode: control-law records start from zero like a calloc'ed trajectory */
+        int i;
+        for (i = 0; i < 2; i++)
+            if (ilqgk_memset(h->w.LL[i], 0, sizeof(double) * (size_t)h->T * h->Bp * h->d.rll, h->stream)) return failk(h);
+    }
     if (ilqgk_launch_init(&h->w, &h->o, h->params, h->stream)) return failk(h);
     h->n_launches++;
     h->iter = 0;
@@ -581,8 +601,8 @@ long ilqgb_get(ilqgb_handle *h, const char *f, double *out)
         lay_t L;
         if (!strcmp(f, "x")) { src = w->XU[0]; alt = w->XU[1]; sel = w->cur; n_k = h->T + 1; n_i = d->nx; L = lay_rec(h, d->rxu, 0); }
         else if (!strcmp(f, "u")) { src = w->XU[0]; alt = w->XU[1]; sel = w->cur; n_k = h->T; n_i = d->nu; L = lay_rec(h, d->rxu, d->nx); }
-        else if (!strcmp(f, "l")) { src = w->LL; n_k = h->T; n_i = d->nu; L = lay_rec(h, d->rll, 0); }
-        else if (!strcmp(f, "L")) { src = w->LL; n_k = h->T; n_i = d->nu * d->nx; L = lay_rec(h, d->rll, d->nu); }
+        else if (!strcmp(f, "l")) { src = w->LL[0]; alt = w->LL[1]; sel = w->cur; n_k = h->T; n_i = d->nu; L = lay_rec(h, d->rll, 0); }
+        else if (!strcmp(f, "L")) { src = w->LL[0]; alt = w->LL[1]; sel = w->cur; n_k = h->T; n_i = d->nu * d->nx; L = lay_rec(h, d->rll, d->nu); }
         else if (!strcmp(f, "v1")) { src = w->V1; n_k = h->T; n_i = d->nv1; L = lay_soa(h, n_i); }
         else if (!strcmp(f, "v2") && d->full_ddp) { src = w->V2; n_k = h->T; n_i = d->nv2; L = lay_soa(h, n_i); }
         else if (!strcmp(f, "fd")) { src = w->FD; n_k = 1; n_i = d->nx + d->nqxx; L = lay_soa(h, n_i); }

@@ -615,7 +615,7 @@ __global__ void __launch_bounds__(BP_BLOCK, ILQG_BP_MINBLOCKS) k_backpass(Work w
                 for (int i = 0; i < NU * NX; i++) rec[NU + i] = Lk[i];
 #pragma unroll
                 for (int i = NU + NU * NX; i < RLL; i++) rec[i] = 0.0;
-                st_rec<RLL>(w.LL + ((size_t)k * Bp + b) * RLL, rec);
+                st_rec<RLL>(w.LL[cur] + ((size_t)k * Bp + b) * RLL, rec);
             }
             /* expected reduction (back_pass.c:204-214) */
 #pragma unroll
@@ -711,7 +711,7 @@ __device__ __forceinline__ bool rollout(const Work &w, const ParamBlock<P> &pb, 
     for (int k = 0; k < T; k++) {
         double nom[RXU], ll[RLL];
         ld_rec<NX + NU>(w.XU[from] + ((size_t)k * Bp + b) * RXU, nom);
-        if (alpha != 0.0) ld_rec<NU + NU * NX>(w.LL + ((size_t)k * Bp + b) * RLL, ll);
+        if (alpha != 0.0) ld_rec<NU + NU * NX>(w.LL[from] + ((size_t)k * Bp + b) * RLL, ll);
         if (alpha != 0.0) {
 #pragma unroll
             for (int j = 0; j < NU; j++) u[j] = nom[NX + j] + ll[j] * alpha;

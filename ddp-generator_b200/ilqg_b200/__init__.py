@@ -20,6 +20,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_DIR = os.environ.get("ILQG_LIB_DIR") or os.path.join(os.path.dirname(_HERE), "lib")
 TRACE, TIMING = 1, 2
 KERNEL_CLASSES = ("derivs", "backpass", "linesearch", "post")
+_SCALAR_FIELDS = {"cost", "new_cost", "dcost", "expected", "lambda", "dlambda", "g_norm", "dV0", "dV1", "w_pen_l", "w_pen_f",
+                  "iterations", "result", "status", "n_linesearch", "n_backpass", "n_derivs", "n_rollouts", "cur"}
 
 
 def lib_path(problem, full_ddp):
@@ -63,6 +65,8 @@ class Library:
         L.ilqgb_set_opt.restype = cp
         L.ilqgb_set_opt.argtypes = [vp, cp, dp, ci]
         L.ilqgb_set_param.argtypes = [vp, ci, dp, ci]
+        L.ilqgb_validate_opt.restype = cp
+        L.ilqgb_validate_opt.argtypes = [cp, dp, ci]
         L.ilqgb_upload.argtypes = [vp, dp, dp]
         for f in ("ilqgb_start", "ilqgb_finish", "ilqgb_solve", "ilqgb_sync", "ilqgb_active", "ilqgb_phase_derivs",
                   "ilqgb_phase_backpass", "ilqgb_phase_linesearch"):
@@ -82,6 +86,12 @@ class Library:
         self.param_names = [L.ilqgb_param_name(i).decode() for i in range(L.ilqgb_n_params())]
         self.param_sizes = [L.ilqgb_param_size(i) for i in range(L.ilqgb_n_params())]
         self.deriv_doubles_per_step = L.ilqgb_deriv_doubles_per_step()
+
+    def validate_option(self, name, value):
+        """setOptParam's check without a handle: None or the reference's message."""
+        v = np.ascontiguousarray(np.atleast_1d(np.asarray(value, dtype=np.float64)))
+        err = self.lib.ilqgb_validate_opt(name.encode(), _ptr(v), v.size)
+        return err.decode() if err else None
 
     def device_count(self):
         return self.lib.ilqgb_device_count()
@@ -198,14 +208,14 @@ class BatchSolver:
         out = buf[:n].copy()
         if field in shapes:
             return out.reshape(shapes[field])
-        return out.reshape(B, -1) if n > B else out
+        return out if field in _SCALAR_FIELDS else out.reshape(B, -1)
 
     def get_int(self, field):
         n_max = self.B * max(self.T, self.max_iter + 1) + 64
         buf = np.empty(n_max, np.int32)
         n = self._chk(self.lib.ilqgb_get_int(self.h, field.encode(), _ptr(buf)))
         out = buf[:n].copy()
-        return out.reshape(self.B, -1) if n > self.B else out
+        return out if field in _SCALAR_FIELDS else out.reshape(self.B, -1)
 
     def launch_count(self):
         return int(self.lib.ilqgb_launch_count(self.h))

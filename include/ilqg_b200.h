@@ -54,6 +54,7 @@ const char *ilqgb_last_error(const ilqgb_handle *h); /* h may be NULL for creati
 /* options and parameters (shared by the whole batch) */
 void ilqgb_standard_parameters(ilqgb_handle *h);
 const char *ilqgb_set_opt(ilqgb_handle *h, const char *name, const double *value, int n); /* NULL = ok */
+const char *ilqgb_validate_opt(const char *name, const double *value, int n);               /* same check, no handle */
 int ilqgb_set_param(ilqgb_handle *h, int index, const double *value, int n);
 
 /* host -> device: x0 [batch][nx], u_nom [batch][n_hor][nu] (problem-major, as a caller holds them) */

@@ -1,0 +1,135 @@
+"""Generate the golden fixtures under tests/golden/ from the UNMODIFIED reference solver core (oracle/_ref, built in
+place from /root/reference by oracle/Makefile).  Run in the build container:  python tests/golden/make_golden.py
+The fixtures pin (a) the oracle port and (b) the CUDA path on machines where /root/reference does not exist.
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "ddp-generator_b200"))
+
+import oracle_lib  # noqa: E402
+import parity_util as PU  # noqa: E402
+from ilqg_b200 import workloads as W  # noqa: E402
+
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+
+def solve_fixture(problem, ddp, T, params, x0, u0, opts, with_qp=False):
+    rec = PU.oracle_record("reference", problem, ddp, T, params, x0, u0, opts, qp_cap=400000 if with_qp else 0)
+    out = {k: np.asarray(v) for k, v in rec.items() if k != "qp"}
+    if with_qp:
+        ret, nfree, cl = rec["qp"]
+        out["qp_ret_last"] = ret[-T:]
+        out["qp_clamped_last"] = cl[-T:]
+        out["qp_ret_hist"] = np.stack(np.unique(ret, return_counts=True))
+    out["x0"], out["u0"] = np.asarray(x0), np.asarray(u0)
+    return out
+
+
+def kats():
+    """Known-answer tests of the small dense helpers, produced by calling the reference functions directly."""
+    lib = C.CDLL(oracle_lib.lib_path("reference", "car", 0))
+    rng = np.random.default_rng(12345)
+    out = {}
+    sym = lambda n: (n * (n + 1)) // 2
+    lib.addMulVec.argtypes = [_dp, _dp, _dp, C.c_int, C.c_int]
+    lib.addSquareTri.argtypes = [_dp, _dp, _dp, C.c_int, C.c_int, _dp]
+    lib.addMul2Tri.argtypes = [_dp, _dp, _dp, C.c_int, C.c_int, _dp, C.c_int, C.c_int, _dp]
+    lib.cholesky_tri.argtypes = [_dp, C.c_int, _dp]
+    lib.cholesky_tri_inv.argtypes = [_dp, _dp, C.c_int, _dp]
+    lib.boxQP.argtypes = [_dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _ip, _dp, C.c_int]
+    cases = []
+    for case, (nr, nc) in enumerate([(4, 2), (4, 4), (2, 4), (12, 4), (1, 1), (3, 5)]):
+        a = rng.standard_normal(nr * nc)
+        Bm = rng.standard_normal(sym(nr))
+        v = rng.standard_normal(nr)
+        base1 = rng.standard_normal(nc)
+        r1 = base1.copy(); lib.addMulVec(r1, v, a, nr, nc)
+        base2 = rng.standard_normal(sym(nc))
+        r2 = base2.copy(); lib.addSquareTri(r2, Bm, a, nr, nc, np.zeros(nr * nc))
+        ncc = 3
+        c = rng.standard_normal(nr * ncc)
+        base3 = rng.standard_normal(nc * ncc)
+        r3 = base3.copy(); lib.addMul2Tri(r3, Bm, a, nr, nc, c, nr, ncc, np.zeros(nr * ncc))
+        out.update({f"mm{case}_dims": np.array([nr, nc, ncc]), f"mm{case}_a": a, f"mm{case}_B": Bm, f"mm{case}_v": v, f"mm{case}_c": c,
+                    f"mm{case}_base1": base1, f"mm{case}_r1": r1, f"mm{case}_base2": base2, f"mm{case}_r2": r2,
+                    f"mm{case}_base3": base3, f"mm{case}_r3": r3})
+        cases.append(case)
+    out["mm_cases"] = np.array(cases)
+    # Cholesky / inverse on SPD and on an indefinite matrix
+    n_ch = 0
+    for n in (1, 2, 3, 4, 6):
+        for trial in range(3):
+            M = rng.standard_normal((n, n + 2))
+            A = M @ M.T + (0.0 if trial < 2 else -3.0) * np.eye(n)
+            Ap = np.array([A[r, c] for c in range(n) for r in range(c + 1)])
+            U = np.zeros(sym(n)); ok = lib.cholesky_tri(Ap, n, U)
+            inv = np.zeros(sym(n))
+            if ok:
+                lib.cholesky_tri_inv(U, inv, n, np.zeros(n))
+            out.update({f"ch{n_ch}_n": np.array([n]), f"ch{n_ch}_A": Ap, f"ch{n_ch}_ok": np.array([ok]), f"ch{n_ch}_U": U, f"ch{n_ch}_inv": inv})
+            n_ch += 1
+    out["ch_count"] = np.array([n_ch])
+    # box QP: random problems incl. tight / inactive bounds and warm starts
+    n_qp = 0
+    for n in (1, 2, 3, 4):
+        for trial in range(12):
+            M = rng.standard_normal((n, n + 1))
+            H = M @ M.T + (1e-3 if trial % 4 else -0.5) * np.eye(n)
+            Hp = np.array([H[r, c] for c in range(n) for r in range(c + 1)])
+            g = rng.standard_normal(n) * (3.0 if trial % 3 == 0 else 0.3)
+            lo = -np.abs(rng.standard_normal(n)) * (0.1 if trial % 2 else 2.0)
+            hi = np.abs(rng.standard_normal(n)) * (0.1 if trial % 5 == 0 else 2.0)
+            if trial == 7:
+                lo[:] = -np.inf; hi[:] = np.inf
+            x = rng.standard_normal(n)
+            x_in = x.copy()
+            clamped = np.zeros(n, np.int32); nfree = np.zeros(1, np.int32)
+            inv = np.zeros(sym(n))
+            ret = lib.boxQP(Hp.copy(), g, lo, hi, x, np.zeros(sym(n)), np.zeros(sym(n)), np.zeros(n), np.zeros(n), np.zeros(n),
+                            clamped, nfree, inv, n)
+            out.update({f"qp{n_qp}_n": np.array([n]), f"qp{n_qp}_H": Hp, f"qp{n_qp}_g": g, f"qp{n_qp}_lo": lo, f"qp{n_qp}_hi": hi,
+                        f"qp{n_qp}_x0": x_in, f"qp{n_qp}_x": x, f"qp{n_qp}_ret": np.array([ret]), f"qp{n_qp}_clamped": clamped,
+                        f"qp{n_qp}_nfree": nfree, f"qp{n_qp}_inv": inv})
+            n_qp += 1
+    out["qp_count"] = np.array([n_qp])
+    return out
+
+
+def main():
+    assert oracle_lib.available("reference", "car", 0), "build oracle/_ref first (make -C oracle ref)"
+    x0, u0 = W.car_single()
+    for ddp in (0, 1):
+        np.savez_compressed(os.path.join(HERE, f"car_single_ddp{ddp}.npz"),
+                            **solve_fixture("car", ddp, 500, W.CAR_PARAMS, x0, u0, {"max_iter": 200}, with_qp=True))
+    xb, ub = W.car_batch(8, T=100, seed=5)
+    for b in range(8):
+        np.savez_compressed(os.path.join(HERE, f"car_T100_b{b}.npz"),
+                            **solve_fixture("car", 0, 100, W.CAR_PARAMS, xb[b], ub[b], {"max_iter": 30}))
+    for n in (2, 3, 5, 500):
+        params, bx0, bu0, opts = W.brachi(n)
+        for ddp in (0, 1):
+            np.savez_compressed(os.path.join(HERE, f"brachi_n{n}_ddp{ddp}.npz"),
+                                **solve_fixture("brachi", ddp, n, params, bx0, bu0, opts))
+    np.savez_compressed(os.path.join(HERE, "kats.npz"), **kats())
+    # bit patterns of the deterministic math layer on a fixed grid
+    lib = C.CDLL(os.path.join(ROOT, "oracle", "_build", "libdmcheck.so"))
+    lib.dmc_vec.argtypes = [C.c_int, _dp, _dp, C.c_long]
+    xs = np.concatenate([np.linspace(-7, 7, 2001), np.linspace(-1e4, 1e4, 501), [0.0, -0.0, 1e-300, 1.5e6, 1.7e6]])
+    xa = np.concatenate([np.linspace(-1, 1, 2001), [0.5, -0.5, 0.975, 1e-9, 1.0000001]])
+    ys = {}
+    for i, (nm, grid) in enumerate([("sin", xs), ("cos", xs), ("asin", xa), ("acos", xa)]):
+        y = np.zeros_like(grid); lib.dmc_vec(i, np.ascontiguousarray(grid), y, grid.size); ys[nm] = y
+    np.savez_compressed(os.path.join(HERE, "dm_math.npz"), xs=xs, xa=xa, **ys)
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()

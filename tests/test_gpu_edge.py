@@ -1,0 +1,117 @@
+"""Edge cases and size-independent properties of the CUDA path (through the C ABI)."""
+import numpy as np
+import pytest
+
+import ilqg_b200
+import oracle_lib
+import parity_util as PU
+from ilqg_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle(problem, ddp):
+    return oracle_lib.OracleLib(PU.oracle_kinds(problem, ddp)[0], problem, ddp)
+
+
+@pytest.mark.parametrize("B", [1, 31, 33, 65])
+def test_ragged_batch_sizes(B):
+    x0, u0 = W.car_batch(B, T=60, seed=21)
+    opts = {"max_iter": 8}
+    s = ilqg_b200.BatchSolver("car", 0, B, 60)
+    s.set_options(opts); s.set_params(W.CAR_PARAMS)
+    out = s.solve(x0, u0)
+    ora = _oracle("car", 0).solve_batch(x0, u0, W.CAR_PARAMS, {"max_iter": 8.0}, 2, want_traj=True)
+    for k in ("cost", "iterations", "n_linesearch", "x", "u"):
+        assert np.array_equal(out[k], ora[k]), k
+    assert np.array_equal(out["success"], ora["result"])
+    s.close()
+
+
+@pytest.mark.parametrize("opts", [{"max_iter": 0}, {"max_iter": 1}, {"max_iter": 12, "zMin": 0.5}, {"max_iter": 12, "alpha": [1.0, 0.1]},
+                                   {"max_iter": 12, "alpha": [0.5]}, {"max_iter": 15, "lambdaInit": 100.0, "lambdaMax": 1000.0},
+                                   {"max_iter": 12, "lambdaFactor": 3.0, "lambdaMin": 1e-3, "dlambdaInit": 2.0},
+                                   {"max_iter": 40, "tolFun": 1e-2}, {"max_iter": 40, "tolGrad": 1.0, "lambdaInit": 1e-6}])
+def test_options_follow_reference(opts):
+    B, T = 6, 80
+    x0, u0 = W.car_batch(B, T=T, seed=31)
+    recs = PU.gpu_records("car", 0, T, W.CAR_PARAMS, x0, u0, opts)
+    kind = PU.oracle_kinds("car", 0)[0]
+    for b in range(B):
+        if opts["max_iter"] == 0:
+            continue   # backPassDone is uninitialised in the reference for max_iter == 0: result undefined
+        ora = PU.oracle_record(kind, "car", 0, T, W.CAR_PARAMS, x0[b], u0[b], opts)
+        PU.assert_same(recs[b], ora, f"opts {opts} b{b}")
+    if opts["max_iter"] == 0:
+        assert all(r["iterations"] == 0 and r["n_ls"] == 0 for r in recs)
+
+
+def test_failed_initial_rollout_is_reported():
+    """A rollout whose dynamics turn non-finite makes the harness/mex report failure before iLQG starts
+    (iLQG_mex.c:116-118): result -1 here, and the problem takes no passes."""
+    B, T = 4, 30
+    x0, u0 = W.car_batch(B, T=T, seed=41)
+    x0[2, 3] = 1e4    # speed so large that sqrt(d^2 - (h v sin w)^2) is NaN
+    s = ilqg_b200.BatchSolver("car", 0, B, T)
+    s.set_options({"max_iter": 5}); s.set_params(W.CAR_PARAMS)
+    out = s.solve(x0, u0)
+    O = _oracle("car", 0)
+    for b in range(B):
+        h = O.solver(T); h.set_opts({"max_iter": 5}); h.set_params(W.CAR_PARAMS)
+        ok = h.init(x0[b], u0[b])
+        assert (out["success"][b] == -1) == (not ok)
+        if ok:
+            h.solve()
+            assert out["cost"][b] == h.scalar("cost") and out["iterations"][b] == h.scalar("iterations")
+    assert out["n_linesearch"][2] == 0
+    s.close()
+
+
+def test_all_controls_clamped_and_limits():
+    """Controls far outside the box: the initial rollout clamps them and most QPs return 6."""
+    B, T = 3, 50
+    x0, u0 = W.car_batch(B, T=T, seed=51)
+    u0 = u0 * 100.0
+    recs = PU.gpu_records("car", 0, T, W.CAR_PARAMS, x0, u0, {"max_iter": 6})
+    kind = PU.oracle_kinds("car", 0)[0]
+    for b in range(B):
+        ora = PU.oracle_record(kind, "car", 0, T, W.CAR_PARAMS, x0[b], u0[b], {"max_iter": 6})
+        PU.assert_same(recs[b], ora, f"clamped b{b}")
+        assert np.abs(recs[b]["u"][:, 0]).max() <= 0.5 and np.abs(recs[b]["u"][:, 1]).max() <= 2.0
+
+
+def test_properties_at_config3_size():
+    """BASELINE config 3 (B = 4096, T = 500): determinism, batch-composition invariance, monotone cost."""
+    B, T = 4096, 500
+    x0, u0 = W.car_batch(B, T=T)
+    s = ilqg_b200.BatchSolver("car", 0, B, T, flags=ilqg_b200.TRACE)
+    s.set_options({"max_iter": 12}); s.set_params(W.CAR_PARAMS)
+    a = s.solve(x0, u0)
+    tr_cost, tr_alpha = s.get("tr_newcost"), s.get_int("tr_alpha")
+    cost0 = None
+    b2 = s.solve(x0, u0)
+    for k in ("cost", "iterations", "n_linesearch", "x", "u"):
+        assert np.array_equal(a[k], b2[k]), f"rerun differs in {k}"
+    # permuting the problems permutes the results
+    perm = np.random.default_rng(0).permutation(B)
+    c = s.solve(x0[perm], u0[perm])
+    for k in ("cost", "iterations", "n_linesearch", "x", "u"):
+        assert np.array_equal(c[k], a[k][perm]), f"permutation changes {k}"
+    s.close()
+    # a problem's result does not depend on which batch it is in
+    sub = np.arange(100, 100 + 37)
+    t = ilqg_b200.BatchSolver("car", 0, sub.size, T)
+    t.set_options({"max_iter": 12}); t.set_params(W.CAR_PARAMS)
+    d = t.solve(x0[sub], u0[sub])
+    for k in ("cost", "iterations", "x", "u"):
+        assert np.array_equal(d[k], a[k][sub]), k
+    t.close()
+    # every accepted step lowers the cost: accepted new_cost sequence is strictly decreasing per problem
+    n_alpha = 8
+    for b in range(0, B, 97):
+        n = a["n_linesearch"][b]
+        acc = tr_cost[b][:n][tr_alpha[b][:n] <= n_alpha]
+        assert np.all(np.diff(acc) < 0)
+    # and 64 of them against the oracle
+    ora = _oracle("car", 0).solve_batch(x0[:64], u0[:64], W.CAR_PARAMS, {"max_iter": 12.0}, 4, want_traj=True)
+    assert np.array_equal(ora["cost"], a["cost"][:64]) and np.array_equal(ora["x"], a["x"][:64])

@@ -1,0 +1,49 @@
+"""CUDA path vs the committed golden fixtures (recorded from the unmodified reference core): no oracle library
+needed at run time.  Bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+import parity_util as PU
+from ilqg_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+KEYS = ("result", "iterations", "n_ls", "n_bp", "cost", "lambda", "g_norm", "w_pen_l", "w_pen_f", "dV0", "dV1",
+        "tr_alpha", "tr_lambda", "tr_newcost", "x", "u", "l", "L")
+
+
+def test_car_golden_batch():
+    """All car fixtures with T=100 as ONE batch: ragged convergence inside a batch must not disturb any problem."""
+    gs = [np.load(os.path.join(GOLD, f"car_T100_b{b}.npz")) for b in range(8)]
+    x0 = np.stack([g["x0"] for g in gs])
+    u0 = np.stack([g["u0"] for g in gs])
+    recs = PU.gpu_records("car", 0, 100, W.CAR_PARAMS, x0, u0, {"max_iter": 30})
+    for b, g in enumerate(gs):
+        PU.assert_same(recs[b], {k: g[k] for k in KEYS}, f"car_T100_b{b}", keys=KEYS)
+
+
+@pytest.mark.parametrize("ddp", [0, 1])
+def test_car_single_golden(ddp):
+    g = np.load(os.path.join(GOLD, f"car_single_ddp{ddp}.npz"))
+    rec = PU.gpu_records("car", ddp, 500, W.CAR_PARAMS, g["x0"], g["u0"], {"max_iter": 200})[0]
+    PU.assert_same(rec, {k: g[k] for k in KEYS}, f"car_single_ddp{ddp}", keys=KEYS)
+    if (g["qp_ret_last"] >= 1).all():
+        code = rec["tr_clamp"]
+        assert np.array_equal(np.stack([code & 3, (code >> 2) & 3], axis=1)[::-1], g["qp_clamped_last"])
+        assert np.array_equal(((code >> 16) & 0xff)[::-1], g["qp_ret_last"])
+
+
+@pytest.mark.parametrize("n", [2, 3, 5, 500])
+@pytest.mark.parametrize("ddp", [0, 1])
+def test_brachi_golden(n, ddp):
+    g = np.load(os.path.join(GOLD, f"brachi_n{n}_ddp{ddp}.npz"))
+    params, _, _, opts = W.brachi(n)
+    rec = PU.gpu_records("brachi", ddp, n, params, g["x0"][None], g["u0"][None], opts)[0]
+    PU.assert_same(rec, {k: g[k] for k in KEYS}, f"brachi n={n} ddp{ddp}", keys=KEYS)
+    import ilqg_b200  # final multiplier mu_fe and its trace end state
+    s = ilqg_b200.BatchSolver("brachi", ddp, 1, n)
+    s.set_options(opts); s.set_params(params); s.solve(g["x0"][None], g["u0"][None])
+    assert s.get("mu_f").ravel()[0] == g["mult_f"][0]
+    s.close()
