@@ -62,6 +62,8 @@ int ilqgk_stream_create(void **s) { cudaStream_t st; int r = check(cudaStreamCre
 int ilqgk_stream_destroy(void *s) { return check(cudaStreamDestroy((cudaStream_t)s), "cudaStreamDestroy"); }
 int ilqgk_stream_sync(void *s) { return check(cudaStreamSynchronize((cudaStream_t)s), "cudaStreamSynchronize"); }
 int ilqgk_event_create(void **e) { cudaEvent_t ev; int r = check(cudaEventCreate(&ev), "cudaEventCreate"); *e = (void *)ev; return r; }
+int ilqgk_event_create_notiming(void **e) { cudaEvent_t ev; int r = check(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreate"); *e = (void *)ev; return r; }
+int ilqgk_stream_wait_event(void *s, void *e) { return check(cudaStreamWaitEvent((cudaStream_t)s, (cudaEvent_t)e, 0), "cudaStreamWaitEvent"); }
 int ilqgk_event_destroy(void *e) { return check(cudaEventDestroy((cudaEvent_t)e), "cudaEventDestroy"); }
 int ilqgk_event_record(void *e, void *s) { return check(cudaEventRecord((cudaEvent_t)e, (cudaStream_t)s), "cudaEventRecord"); }
 int ilqgk_event_elapsed(void *a, void *b, float *ms) { return check(cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b), "cudaEventElapsedTime"); }

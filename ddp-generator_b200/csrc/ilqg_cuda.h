@@ -32,6 +32,8 @@ int ilqgk_stream_create(void **s);
 int ilqgk_stream_destroy(void *s);
 int ilqgk_stream_sync(void *s);
 int ilqgk_event_create(void **e);
+int ilqgk_event_create_notiming(void **e);
+int ilqgk_stream_wait_event(void *s, void *e);
 int ilqgk_event_destroy(void *e);
 int ilqgk_event_record(void *e, void *s);
 int ilqgk_event_elapsed(void *a, void *b, float *ms);

@@ -22,7 +22,8 @@ typedef struct {
     int cls;
 } ev_pair;
 
-struct ilqgb_handle {
+typedef struct chunk chunk;
+struct chunk {
     int device, B, Bp, T, flags;
     ilqgk_dims_t d;
     ilqg_work w;
@@ -48,16 +49,17 @@ struct ilqgb_handle {
 };
 
 static char g_create_err[256] = "";
+#define fail_create(msg) (snprintf(g_create_err, sizeof g_create_err, "%s", msg), (void)0)
 
-static int fail(ilqgb_handle *h, const char *msg)
+static int fail(chunk *h, const char *msg)
 {
     snprintf(h ? h->err : g_create_err, 256, "%s", msg);
     return -1;
 }
 
-static int failk(ilqgb_handle *h) { return fail(h, ilqgk_last_error()); }
+static int failk(chunk *h) { return fail(h, ilqgk_last_error()); }
 
-static void *dalloc(ilqgb_handle *h, size_t bytes)
+static void *dalloc(chunk *h, size_t bytes)
 {
     void *p = NULL;
     if (ilqgk_malloc(&p, bytes)) {
@@ -83,12 +85,12 @@ int ilqgb_param_size(int i) { return ilqgk_param_size(i); }
 int ilqgb_device_count(void) { return ilqgk_device_count(); }
 int ilqgb_deriv_doubles_per_step(void) { ilqgk_dims_t d; ilqgk_dims(&d); return d.nv1 + (d.full_ddp ? d.nv2 : 0); }
 
-const char *ilqgb_last_error(const ilqgb_handle *h) { return h ? h->err : g_create_err; }
+static void ck_destroy(chunk *h);
 
 /* ---- options (reference: standard_parameters iLQG.c:57-78, setOptParam iLQG.c:91-216) ----------------------------------- */
 static const double k_alpha_default[8] = {1.0, 0.3727594, 0.1389495, 0.0517947, 0.0193070, 0.0071969, 0.0026827, 0.0010000};
 
-void ilqgb_standard_parameters(ilqgb_handle *h)
+static void ck_standard_parameters(chunk *h)
 {
     ilqg_opts *o = &h->o;
     memset(o, 0, sizeof *o);
@@ -170,7 +172,7 @@ const char *ilqgb_validate_opt(const char *name, const double *value, int n)
     return "no such parameter";
 }
 
-const char *ilqgb_set_opt(ilqgb_handle *h, const char *name, const double *value, int n)
+static const char *ck_set_opt(chunk *h, const char *name, const double *value, int n)
 {
     size_t i;
     const char *msg = ilqgb_validate_opt(name, value, n);
@@ -192,7 +194,7 @@ const char *ilqgb_set_opt(ilqgb_handle *h, const char *name, const double *value
     return NULL; /* debug_level */
 }
 
-int ilqgb_set_param(ilqgb_handle *h, int index, const double *value, int n)
+static int ck_set_param(chunk *h, int index, const double *value, int n)
 {
     int i, off = 0;
     if (index < 0 || index >= ilqgk_param_count()) return fail(h, "parameter index out of range");
@@ -211,9 +213,9 @@ int ilqgb_set_param(ilqgb_handle *h, int index, const double *value, int n)
         if (!(dst)) goto oom;                                      \
     } while (0)
 
-ilqgb_handle *ilqgb_create(int device, int batch, int n_hor, int flags, void *stream)
+static chunk *ck_create(int device, int batch, int n_hor, int flags, void *stream)
 {
-    ilqgb_handle *h;
+    chunk *h;
     size_t Bp, T = (size_t)n_hor;
     if (batch < 1 || n_hor < 1) {
         fail(NULL, "batch and n_hor must be >= 1");
@@ -227,7 +229,7 @@ ilqgb_handle *ilqgb_create(int device, int batch, int n_hor, int flags, void *st
         failk(NULL);
         return NULL;
     }
-    h = (ilqgb_handle *)calloc(1, sizeof *h);
+    h = (chunk *)calloc(1, sizeof *h);
     h->device = device;
     h->B = batch;
     h->Bp = (batch + 31) / 32 * 32;
@@ -240,7 +242,7 @@ ilqgb_handle *ilqgb_create(int device, int batch, int n_hor, int flags, void *st
         return NULL;
     }
     h->params = (double *)calloc((size_t)(h->d.npf > 0 ? h->d.npf : 1), sizeof(double));
-    ilqgb_standard_parameters(h);
+    ck_standard_parameters(h);
     if (stream) {
         h->stream = stream;
     } else {
@@ -307,11 +309,11 @@ ilqgb_handle *ilqgb_create(int device, int batch, int n_hor, int flags, void *st
     return h;
 oom:
     snprintf(g_create_err, sizeof g_create_err, "%s", h->err[0] ? h->err : ilqgk_last_error());
-    ilqgb_destroy(h);
+    ck_destroy(h);
     return NULL;
 }
 
-void ilqgb_destroy(ilqgb_handle *h)
+static void ck_destroy(chunk *h)
 {
     int i;
     if (!h) return;
@@ -330,7 +332,7 @@ void ilqgb_destroy(ilqgb_handle *h)
     free(h);
 }
 
-static int ensure_stage(ilqgb_handle *h, size_t doubles)
+static int ensure_stage(chunk *h, size_t doubles)
 {
     if (doubles <= h->stage_doubles) return 0;
     /* the old staging buffer stays in the allocation list and is freed with the handle */
@@ -343,7 +345,7 @@ static int ensure_stage(ilqgb_handle *h, size_t doubles)
     return 0;
 }
 
-static int ensure_traces(ilqgb_handle *h)
+static int ensure_traces(chunk *h)
 {
     size_t n;
     const int need = h->o.max_iter > 0 ? h->o.max_iter : 1;
@@ -358,7 +360,7 @@ static int ensure_traces(ilqgb_handle *h)
 }
 
 /* ---- data movement ------------------------------------------------------------------------------------------------------------ */
-int ilqgb_upload(ilqgb_handle *h, const double *x0, const double *u_nom)
+static int ck_upload(chunk *h, const double *x0, const double *u_nom)
 {
     const size_t B = (size_t)h->B, T = (size_t)h->T, nx = (size_t)h->d.nx, nu = (size_t)h->d.nu;
     if (ilqgk_set_device(h->device)) return failk(h);
@@ -377,10 +379,10 @@ typedef struct {
     long long stride_k, stride_b, stride_i, off;
 } lay_t;
 
-static lay_t lay_rec(const ilqgb_handle *h, int rec, int off) { lay_t l = {(long long)h->Bp * rec, rec, 1, off}; return l; }
-static lay_t lay_soa(const ilqgb_handle *h, int n_i) { lay_t l = {(long long)h->Bp * n_i, 1, h->Bp, 0}; return l; }
+static lay_t lay_rec(const chunk *h, int rec, int off) { lay_t l = {(long long)h->Bp * rec, rec, 1, off}; return l; }
+static lay_t lay_soa(const chunk *h, int n_i) { lay_t l = {(long long)h->Bp * n_i, 1, h->Bp, 0}; return l; }
 
-static int gather_to_host(ilqgb_handle *h, const double *src, const double *alt, const int *sel, int n_k, int n_i, lay_t L, double *out)
+static int gather_to_host(chunk *h, const double *src, const double *alt, const int *sel, int n_k, int n_i, lay_t L, double *out)
 {
     const size_t n = (size_t)h->B * n_k * n_i;
     if (!n) return 0;
@@ -391,7 +393,7 @@ static int gather_to_host(ilqgb_handle *h, const double *src, const double *alt,
     return 0;
 }
 
-int ilqgb_download(ilqgb_handle *h, double *x, double *u, double *cost, int *iterations, int *result, int *n_linesearch)
+static int ck_download(chunk *h, double *x, double *u, double *cost, int *iterations, int *result, int *n_linesearch)
 {
     const size_t B = (size_t)h->B;
     if (ilqgk_set_device(h->device)) return failk(h);
@@ -413,7 +415,7 @@ int ilqgb_download(ilqgb_handle *h, double *x, double *u, double *cost, int *ite
 }
 
 /* ---- timing -------------------------------------------------------------------------------------------------------------------- */
-static ev_pair *timing_begin(ilqgb_handle *h, int cls)
+static ev_pair *timing_begin(chunk *h, int cls)
 {
     ev_pair *p;
     if (!(h->flags & ILQGB_TIMING)) return NULL;
@@ -432,12 +434,12 @@ static ev_pair *timing_begin(ilqgb_handle *h, int cls)
     return p;
 }
 
-static void timing_end(ilqgb_handle *h, ev_pair *p)
+static void timing_end(chunk *h, ev_pair *p)
 {
     if (p) ilqgk_event_record(p->stop, h->stream);
 }
 
-int ilqgb_timing(ilqgb_handle *h, double *ms, long *launches, int reset)
+static int ck_timing(chunk *h, double *ms, long *launches, int reset)
 {
     int i;
     if (ilqgk_set_device(h->device)) return failk(h);
@@ -462,7 +464,7 @@ int ilqgb_timing(ilqgb_handle *h, double *ms, long *launches, int reset)
 }
 
 /* ---- the solve ------------------------------------------------------------------------------------------------------------------ */
-int ilqgb_start(ilqgb_handle *h)
+static int ck_start(chunk *h)
 {
     if (ilqgk_set_device(h->device)) return failk(h);
     if (ensure_traces(h)) return -1;
@@ -478,7 +480,7 @@ int ilqgb_start(ilqgb_handle *h)
     return 0;
 }
 
-static int launch_pass(ilqgb_handle *h, int do_derivs, int do_back, int do_ls)
+static int launch_pass(chunk *h, int do_derivs, int do_back, int do_ls)
 {
     ev_pair *p;
     if (do_derivs) {
@@ -508,7 +510,7 @@ static int launch_pass(ilqgb_handle *h, int do_derivs, int do_back, int do_ls)
     return 0;
 }
 
-int ilqgb_active(ilqgb_handle *h)
+static int ck_active(chunk *h)
 {
     if (ilqgk_set_device(h->device)) return failk(h);
     if (ilqgk_launch_count_active(&h->w, h->d_counter, h->stream)) return failk(h);
@@ -518,17 +520,17 @@ int ilqgb_active(ilqgb_handle *h)
     return *h->h_counter;
 }
 
-int ilqgb_iterate(ilqgb_handle *h, int n_passes)
+__attribute__((unused)) static int ck_iterate(chunk *h, int n_passes)
 {
     int done = 0;
-    if (!h->started) return fail(h, "ilqgb_start has not been called");
+    if (!h->started) return fail(h, "ck_start has not been called");
     if (ilqgk_set_device(h->device)) return failk(h);
     while (done < n_passes && h->iter < h->o.max_iter) {
         if (launch_pass(h, 1, 1, 1)) return -1;
         h->iter++;
         done++;
         if (h->iter % ACTIVE_CHECK_EVERY == 0 && h->iter < h->o.max_iter) {
-            const int a = ilqgb_active(h);
+            const int a = ck_active(h);
             if (a < 0) return -1;
             if (a == 0) break;
         }
@@ -536,7 +538,7 @@ int ilqgb_iterate(ilqgb_handle *h, int n_passes)
     return done;
 }
 
-int ilqgb_finish(ilqgb_handle *h)
+static int ck_finish(chunk *h)
 {
     if (ilqgk_set_device(h->device)) return failk(h);
     /* problems that are still running after max_iter passes: iLQG.c:365-377 */
@@ -544,14 +546,14 @@ int ilqgb_finish(ilqgb_handle *h)
     return 0;
 }
 
-int ilqgb_solve(ilqgb_handle *h)
+__attribute__((unused)) static int ck_solve(chunk *h)
 {
-    if (ilqgb_start(h)) return -1;
+    if (ck_start(h)) return -1;
     while (h->iter < h->o.max_iter) {
-        const int n = ilqgb_iterate(h, h->o.max_iter - h->iter);
+        const int n = ck_iterate(h, h->o.max_iter - h->iter);
         if (n < 0) return -1;
         if (h->iter < h->o.max_iter) { /* stopped early: everything converged */
-            if (ilqgb_active(h) == 0) break;
+            if (ck_active(h) == 0) break;
         }
     }
     /* when the loop ran out of passes, or max_iter == 0, mark the stragglers */
@@ -559,20 +561,20 @@ int ilqgb_solve(ilqgb_handle *h)
     return 0;
 }
 
-long ilqgb_launch_count(const ilqgb_handle *h) { return h->n_launches; }
+static long ck_launch_count(const chunk *h) { return h->n_launches; }
 
-int ilqgb_sync(ilqgb_handle *h)
+static int ck_sync(chunk *h)
 {
     if (ilqgk_set_device(h->device)) return failk(h);
     return ilqgk_stream_sync(h->stream) ? failk(h) : 0;
 }
 
-int ilqgb_phase_derivs(ilqgb_handle *h) { return ilqgk_set_device(h->device) ? failk(h) : launch_pass(h, 1, 0, 0); }
-int ilqgb_phase_backpass(ilqgb_handle *h) { return ilqgk_set_device(h->device) ? failk(h) : launch_pass(h, 0, 1, 0); }
-int ilqgb_phase_linesearch(ilqgb_handle *h) { return ilqgk_set_device(h->device) ? failk(h) : launch_pass(h, 0, 0, 1); }
+static int ck_phase_derivs(chunk *h) { return ilqgk_set_device(h->device) ? failk(h) : launch_pass(h, 1, 0, 0); }
+static int ck_phase_backpass(chunk *h) { return ilqgk_set_device(h->device) ? failk(h) : launch_pass(h, 0, 1, 0); }
+static int ck_phase_linesearch(chunk *h) { return ilqgk_set_device(h->device) ? failk(h) : launch_pass(h, 0, 0, 1); }
 
 /* ---- read-back -------------------------------------------------------------------------------------------------------------------- */
-long ilqgb_get(ilqgb_handle *h, const char *f, double *out)
+static long ck_get(chunk *h, const char *f, double *out)
 {
     const ilqg_work *w = &h->w;
     const ilqgk_dims_t *d = &h->d;
@@ -617,7 +619,7 @@ long ilqgb_get(ilqgb_handle *h, const char *f, double *out)
     }
 }
 
-long ilqgb_get_int(ilqgb_handle *h, const char *f, int *out)
+static long ck_get_int(chunk *h, const char *f, int *out)
 {
     const ilqg_work *w = &h->w;
     const size_t B = (size_t)h->B, Bp = (size_t)h->Bp;
@@ -653,3 +655,305 @@ long ilqgb_get_int(ilqgb_handle *h, const char *f, int *out)
         return (long)(B * n_k);
     }
 }
+
+
+/* =====================================================================================================================
+ * Public handle: the batch is split into contiguous chunks, each a complete single-stream solver (above) on its own
+ * CUDA stream.  Chunks are independent (problems never interact), so the GPU overlaps the latency-bound tails of
+ * one chunk (late line-search rounds with few undecided problems) with the wide kernels of another, and uploads /
+ * downloads of one chunk with the compute of the others.  Work enqueued by one API call is ordered in the handle's
+ * main stream: chunk streams fork from it at entry and join it at exit.
+ * ===================================================================================================================== */
+#define MAX_CHUNKS 16
+struct ilqgb_handle {
+    int n, device, B, T, flags;
+    chunk *c[MAX_CHUNKS];
+    int first[MAX_CHUNKS];
+    void *stream;      /* main stream (caller's or owned) */
+    int owns_stream;
+    void *ev_fork, *ev_join[MAX_CHUNKS];
+    ilqgk_dims_t d;
+    char err[256];
+};
+
+static int auto_chunks(int batch)
+{
+    int n = batch / 32768;   /* keep >= 32768 problems (1024 warps) per chunk so each kernel still fills the GPU */
+    if (n < 1) n = 1;
+    if (n > 4) n = 4;
+    return n;
+}
+
+static int hfail(ilqgb_handle *h, const chunk *c)
+{
+    snprintf(h->err, sizeof h->err, "%s", c ? c->err : ilqgk_last_error());
+    return -1;
+}
+
+static int fork_streams(ilqgb_handle *h)
+{
+    int i;
+    if (h->n == 1) return 0;
+    if (ilqgk_event_record(h->ev_fork, h->stream)) return hfail(h, NULL);
+    for (i = 0; i < h->n; i++)
+        if (ilqgk_stream_wait_event(h->c[i]->stream, h->ev_fork)) return hfail(h, NULL);
+    return 0;
+}
+
+static int join_streams(ilqgb_handle *h)
+{
+    int i;
+    if (h->n == 1) return 0;
+    for (i = 0; i < h->n; i++) {
+        if (ilqgk_event_record(h->ev_join[i], h->c[i]->stream)) return hfail(h, NULL);
+        if (ilqgk_stream_wait_event(h->stream, h->ev_join[i])) return hfail(h, NULL);
+    }
+    return 0;
+}
+
+const char *ilqgb_last_error(const ilqgb_handle *h) { return h ? h->err : g_create_err; }
+
+ilqgb_handle *ilqgb_create(int device, int batch, int n_hor, int flags, void *stream)
+{
+    ilqgb_handle *h;
+    int i, n = (flags >> 8) & 0xff, per;
+    if (batch < 1 || n_hor < 1) {
+        fail_create("batch and n_hor must be >= 1");
+        return NULL;
+    }
+    if (n == 0) n = auto_chunks(batch);
+    if (n > MAX_CHUNKS) n = MAX_CHUNKS;
+    if (n > batch) n = batch;
+    if (ilqgk_device_count() < 1) {
+        fail_create("no CUDA device available: this library has no CPU fallback");
+        return NULL;
+    }
+    if (ilqgk_set_device(device)) {
+        fail_create(ilqgk_last_error());
+        return NULL;
+    }
+    h = (ilqgb_handle *)calloc(1, sizeof *h);
+    h->n = n; h->device = device; h->B = batch; h->T = n_hor; h->flags = flags;
+    ilqgk_dims(&h->d);
+    if (stream) {
+        h->stream = stream;
+    } else {
+        if (ilqgk_stream_create(&h->stream)) { fail_create(ilqgk_last_error()); free(h); return NULL; }
+        h->owns_stream = 1;
+    }
+    per = ((batch + n - 1) / n + 31) / 32 * 32;   /* chunk sizes are multiples of a warp */
+    for (i = 0; i < n; i++) {
+        const int first = i * per;
+        int cnt = batch - first < per ? batch - first : per;
+        if (cnt <= 0) { h->n = i; break; }
+        h->first[i] = first;
+        h->c[i] = ck_create(device, cnt, n_hor, flags & 0xff, n == 1 ? h->stream : NULL);
+        if (!h->c[i]) { ilqgb_destroy(h); return NULL; }
+    }
+    if (h->n > 1) {
+        if (ilqgk_event_create_notiming(&h->ev_fork)) { fail_create(ilqgk_last_error()); ilqgb_destroy(h); return NULL; }
+        for (i = 0; i < h->n; i++)
+            if (ilqgk_event_create_notiming(&h->ev_join[i])) { fail_create(ilqgk_last_error()); ilqgb_destroy(h); return NULL; }
+    }
+    return h;
+}
+
+void ilqgb_destroy(ilqgb_handle *h)
+{
+    int i;
+    if (!h) return;
+    for (i = 0; i < MAX_CHUNKS; i++) {
+        if (h->c[i]) ck_destroy(h->c[i]);
+        if (h->ev_join[i]) ilqgk_event_destroy(h->ev_join[i]);
+    }
+    if (h->ev_fork) ilqgk_event_destroy(h->ev_fork);
+    if (h->owns_stream && h->stream) ilqgk_stream_destroy(h->stream);
+    free(h);
+}
+
+void ilqgb_standard_parameters(ilqgb_handle *h) { int i; for (i = 0; i < h->n; i++) ck_standard_parameters(h->c[i]); }
+
+const char *ilqgb_set_opt(ilqgb_handle *h, const char *name, const double *value, int n)
+{
+    int i;
+    const char *msg = ilqgb_validate_opt(name, value, n);
+    if (msg) return msg;
+    for (i = 0; i < h->n; i++) ck_set_opt(h->c[i], name, value, n);
+    return NULL;
+}
+
+int ilqgb_set_param(ilqgb_handle *h, int index, const double *value, int n)
+{
+    int i;
+    for (i = 0; i < h->n; i++)
+        if (ck_set_param(h->c[i], index, value, n)) return hfail(h, h->c[i]);
+    return 0;
+}
+
+int ilqgb_upload(ilqgb_handle *h, const double *x0, const double *u_nom)
+{
+    int i;
+    if (fork_streams(h)) return -1;
+    for (i = 0; i < h->n; i++)
+        if (ck_upload(h->c[i], x0 + (size_t)h->first[i] * h->d.nx, u_nom + (size_t)h->first[i] * h->T * h->d.nu)) return hfail(h, h->c[i]);
+    return join_streams(h);
+}
+
+int ilqgb_download(ilqgb_handle *h, double *x, double *u, double *cost, int *iterations, int *result, int *n_linesearch)
+{
+    int i;
+    if (fork_streams(h)) return -1;
+    for (i = 0; i < h->n; i++) {
+        const size_t f = (size_t)h->first[i];
+        if (ck_download(h->c[i], x ? x + f * (h->T + 1) * h->d.nx : NULL, u ? u + f * h->T * h->d.nu : NULL, cost ? cost + f : NULL,
+                        iterations ? iterations + f : NULL, result ? result + f : NULL, n_linesearch ? n_linesearch + f : NULL))
+            return hfail(h, h->c[i]);
+    }
+    return join_streams(h);
+}
+
+int ilqgb_start(ilqgb_handle *h)
+{
+    int i;
+    if (fork_streams(h)) return -1;
+    for (i = 0; i < h->n; i++)
+        if (ck_start(h->c[i])) return hfail(h, h->c[i]);
+    return join_streams(h);
+}
+
+int ilqgb_active(ilqgb_handle *h)
+{
+    int i, tot = 0;
+    for (i = 0; i < h->n; i++) {
+        const int a = ck_active(h->c[i]);
+        if (a < 0) return hfail(h, h->c[i]);
+        tot += a;
+    }
+    return tot;
+}
+
+int ilqgb_iterate(ilqgb_handle *h, int n_passes)
+{
+    int done = 0, i;
+    chunk *c0 = h->c[0];
+    if (!c0->started) { snprintf(h->err, sizeof h->err, "ilqgb_start has not been called"); return -1; }
+    if (ilqgk_set_device(h->device)) return hfail(h, NULL);
+    if (fork_streams(h)) return -1;
+    while (done < n_passes && c0->iter < c0->o.max_iter) {
+        for (i = 0; i < h->n; i++) {   /* issue pass p of every chunk before pass p+1 of any: streams advance together */
+            if (launch_pass(h->c[i], 1, 1, 1)) return hfail(h, h->c[i]);
+            h->c[i]->iter++;
+        }
+        done++;
+        if (c0->iter % ACTIVE_CHECK_EVERY == 0 && c0->iter < c0->o.max_iter) {
+            const int a = ilqgb_active(h);
+            if (a < 0) return -1;
+            if (a == 0) break;
+        }
+    }
+    if (join_streams(h)) return -1;
+    return done;
+}
+
+int ilqgb_finish(ilqgb_handle *h)
+{
+    int i;
+    if (fork_streams(h)) return -1;
+    for (i = 0; i < h->n; i++)
+        if (ck_finish(h->c[i])) return hfail(h, h->c[i]);
+    return join_streams(h);
+}
+
+int ilqgb_solve(ilqgb_handle *h)
+{
+    int i;
+    if (ilqgb_start(h)) return -1;
+    while (h->c[0]->iter < h->c[0]->o.max_iter) {
+        const int n = ilqgb_iterate(h, h->c[0]->o.max_iter - h->c[0]->iter);
+        if (n < 0) return -1;
+        if (h->c[0]->iter < h->c[0]->o.max_iter && ilqgb_active(h) == 0) break;
+    }
+    if (fork_streams(h)) return -1;
+    for (i = 0; i < h->n; i++)   /* problems still running after the last pass hit the iteration limit */
+        if (ilqgk_launch_finalize(&h->c[i]->w, h->c[i]->o.max_iter, h->c[i]->stream)) return hfail(h, NULL);
+    return join_streams(h);
+}
+
+int ilqgb_sync(ilqgb_handle *h)
+{
+    int i;
+    if (ilqgk_set_device(h->device)) return hfail(h, NULL);
+    for (i = 0; i < h->n; i++)
+        if (ck_sync(h->c[i])) return hfail(h, h->c[i]);
+    return ilqgk_stream_sync(h->stream) ? hfail(h, NULL) : 0;
+}
+
+#define FANOUT_PHASE(NAME)                                             \
+    int ilqgb_phase_##NAME(ilqgb_handle *h)                            \
+    {                                                                  \
+        int i;                                                         \
+        if (fork_streams(h)) return -1;                                \
+        for (i = 0; i < h->n; i++)                                     \
+            if (ck_phase_##NAME(h->c[i])) return hfail(h, h->c[i]);    \
+        return join_streams(h);                                        \
+    }
+FANOUT_PHASE(derivs)
+FANOUT_PHASE(backpass)
+FANOUT_PHASE(linesearch)
+
+long ilqgb_get(ilqgb_handle *h, const char *field, double *out)
+{
+    int i;
+    long per = -1, tot = 0;
+    if (ilqgb_sync(h)) return -1;
+    for (i = 0; i < h->n; i++) {
+        long n = ck_get(h->c[i], field, out + (per < 0 ? 0 : (size_t)h->first[i] * per));
+        if (n < 0) return hfail(h, h->c[i]);
+        if (per < 0) per = n / h->c[i]->B;
+        tot += n;
+    }
+    return tot;
+}
+
+long ilqgb_get_int(ilqgb_handle *h, const char *field, int *out)
+{
+    int i;
+    long per = -1, tot = 0;
+    if (ilqgb_sync(h)) return -1;
+    for (i = 0; i < h->n; i++) {
+        long n = ck_get_int(h->c[i], field, out + (per < 0 ? 0 : (size_t)h->first[i] * per));
+        if (n < 0) return hfail(h, h->c[i]);
+        if (per < 0) per = n / h->c[i]->B;
+        tot += n;
+    }
+    return tot;
+}
+
+int ilqgb_timing(ilqgb_handle *h, double *ms, long *launches, int reset)
+{
+    int i, k;
+    double m[TC_N];
+    long l[TC_N];
+    for (k = 0; k < TC_N; k++) {
+        if (ms) ms[k] = 0.0;
+        if (launches) launches[k] = 0;
+    }
+    for (i = 0; i < h->n; i++) {
+        if (ck_timing(h->c[i], m, l, reset)) return hfail(h, h->c[i]);
+        for (k = 0; k < TC_N; k++) {
+            if (ms) ms[k] += m[k];
+            if (launches) launches[k] += l[k];
+        }
+    }
+    return 0;
+}
+
+long ilqgb_launch_count(const ilqgb_handle *h)
+{
+    int i;
+    long n = 0;
+    for (i = 0; i < h->n; i++) n += ck_launch_count(h->c[i]);
+    return n;
+}
+
+int ilqgb_chunks(const ilqgb_handle *h) { return h->n; }

@@ -80,6 +80,7 @@ class Library:
         L.ilqgb_timing.argtypes = [vp, dp, dp, ci]
         L.ilqgb_launch_count.restype = C.c_long
         L.ilqgb_launch_count.argtypes = [vp]
+        L.ilqgb_chunks.argtypes = [vp]
         self.problem = L.ilqgb_problem_name().decode()
         self.nx, self.nu = L.ilqgb_nx(), L.ilqgb_nu()
         self.full_ddp = L.ilqgb_full_ddp()
@@ -98,13 +99,13 @@ class Library:
 
 
 class BatchSolver:
-    def __init__(self, problem, full_ddp=0, batch=1, n_hor=1, device=0, flags=0, stream=None):
+    def __init__(self, problem, full_ddp=0, batch=1, n_hor=1, device=0, flags=0, stream=None, chunks=0):
         self.L = Library(problem, full_ddp)
         self.lib = self.L.lib
         self.B, self.T = int(batch), int(n_hor)
         self.nx, self.nu = self.L.nx, self.L.nu
         self.max_iter = 20
-        self.h = self.lib.ilqgb_create(int(device), self.B, self.T, int(flags), C.c_void_p(stream) if stream else None)
+        self.h = self.lib.ilqgb_create(int(device), self.B, self.T, int(flags) | ((int(chunks) & 0xff) << 8), C.c_void_p(stream) if stream else None)
         if not self.h:
             raise RuntimeError("ilqgb_create failed: " + self.lib.ilqgb_last_error(None).decode())
 
@@ -216,6 +217,9 @@ class BatchSolver:
         n = self._chk(self.lib.ilqgb_get_int(self.h, field.encode(), _ptr(buf)))
         out = buf[:n].copy()
         return out if field in _SCALAR_FIELDS else out.reshape(self.B, -1)
+
+    def chunks(self):
+        return int(self.lib.ilqgb_chunks(self.h))
 
     def launch_count(self):
         return int(self.lib.ilqgb_launch_count(self.h))

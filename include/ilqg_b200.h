@@ -33,7 +33,9 @@ typedef struct ilqgb_handle ilqgb_handle;
 enum {
     ILQGB_TRACE = 1,  /* keep per-iteration lambda / alpha / cost and per-step active sets (parity tests) */
     ILQGB_TIMING = 2  /* record CUDA events around every kernel launch (bench roofline) */
+    /* bits 8..15 of `flags`: number of chunks (concurrent streams) the batch is split into; 0 = automatic */
 };
+#define ILQGB_CHUNKS(n) (((n) & 0xff) << 8)
 
 /* static facts of this library build */
 const char *ilqgb_problem_name(void);
@@ -91,6 +93,7 @@ long ilqgb_get_int(ilqgb_handle *h, const char *field, int *out);
 int ilqgb_timing(ilqgb_handle *h, double *ms, long *launches, int reset);
 /* kernels launched by this handle since creation (all classes, incl. layout and bookkeeping kernels) */
 long ilqgb_launch_count(const ilqgb_handle *h);
+int ilqgb_chunks(const ilqgb_handle *h); /* number of chunks / streams this handle runs on */
 
 #ifdef __cplusplus
 }
