@@ -179,6 +179,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=262144)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunks", type=int, default=0, help="concurrent streams per GPU (0 = automatic)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -233,7 +234,7 @@ def main():
     from ilqg_b200 import workloads as W
 
     stream = torch.cuda.current_stream().cuda_stream
-    S = ilqg_b200.BatchSolver(PROBLEM, FULL_DDP, count, T_HOR, device=local_rank, flags=ilqg_b200.TIMING, stream=stream)
+    S = ilqg_b200.BatchSolver(PROBLEM, FULL_DDP, count, T_HOR, device=local_rank, flags=0, stream=stream, chunks=args.chunks)
     S.set_params(W.CAR_PARAMS)
 
     # ---- warm-up: W passes on the same inputs ------------------------------------------------------------------------------
@@ -241,7 +242,6 @@ def main():
     S.upload_ptr(x0_t.data_ptr(), u0_t.data_ptr())
     S.run()
     S.sync()
-    S.timing(reset=True)
 
     # ---- timed region 1: inputs resident, K passes ---------------------------------------------------------------------------
     S.set_options({"max_iter": args.steps})
@@ -258,12 +258,8 @@ def main():
     clocks = sampler.stop()
     ms_dev = e0.elapsed_time(e1)
     launches = S.launch_count() - launches0
-    ktime = S.timing(reset=True)
     S.download_ptr(None, None, cost_out.data_ptr(), it_out.data_ptr(), res_out.data_ptr(), nls_out.data_ptr())
     n_ls = int(nls_out.numpy().sum())
-    n_dv = int(S.get_int("n_derivs").sum())
-    n_bp = int(S.get_int("n_backpass").sum())
-    n_roll = int(S.get_int("n_rollouts").sum())
     cost_resident = cost_out.numpy().copy()
 
     ms_max = reduce(ms_dev, dist.ReduceOp.MAX if world > 1 else None)
@@ -283,7 +279,6 @@ def main():
     wall_e2e = time.perf_counter() - t0
     ms_e2e = max(e2.elapsed_time(e3), wall_e2e * 1e3)
     barrier()
-    S.timing(reset=True)
     n_ls_e2e = int(nls_out.numpy().sum())
     deterministic = bool(np.array_equal(cost_resident, cost_out.numpy()))
     ms_e2e_max = reduce(ms_e2e, dist.ReduceOp.MAX if world > 1 else None)
@@ -293,12 +288,26 @@ def main():
     h2d_tot = reduce(h2d, dist.ReduceOp.SUM if world > 1 else None)
     d2h_tot = reduce(d2h, dist.ReduceOp.SUM if world > 1 else None)
 
-    # ---- roofline of the dominant kernel (rank 0's shard) ------------------------------------------------------------------
+    # ---- roofline of the dominant kernel: kernels timed ALONE (one stream, CUDA events around every launch) on the
+    #      problems of one chunk of this rank's shard, i.e. at exactly the launch size the timed run uses --------------------
+    n_k = max(1, count // S.chunks())
+    K = ilqg_b200.BatchSolver(PROBLEM, FULL_DDP, n_k, T_HOR, device=local_rank, flags=ilqg_b200.TIMING, stream=stream, chunks=1)
+    K.set_params(W.CAR_PARAMS)
+    K.set_options({"max_iter": args.steps})
+    K.upload_ptr(x0_t.data_ptr(), u0_t.data_ptr())
+    K.run()
+    K.sync()
+    ktime = K.timing(reset=True)
+    n_dv = int(K.get_int("n_derivs").sum())
+    n_bp = int(K.get_int("n_backpass").sum())
+    n_roll = int(K.get_int("n_rollouts").sum())
+    K.close()
     NV = S.L.deriv_doubles_per_step
+    RXU, RLL = 8 * ((nx + nu + 3) // 4) * 4, 8 * ((nu + nu * nx + 3) // 4) * 4      # record sizes in bytes
     alg = {
-        "derivs": n_dv * (T_HOR * (nx + nu + NV) * 8 + (nx + nx + nx * (nx + 1) // 2) * 8),
-        "backpass": n_bp * (T_HOR * (NV + nu + nu + nu * nx) * 8 + (nx + nx * (nx + 1) // 2) * 8),
-        "linesearch": n_roll * T_HOR * ((nx + nu + nu + nu * nx) + (nx + nu)) * 8,
+        "derivs": n_dv * (T_HOR * (RXU + NV * 8) + (RXU + (nx + nx * (nx + 1) // 2) * 8)),
+        "backpass": n_bp * (T_HOR * (NV * 8 + nu * 8 + RLL) + (nx + nx * (nx + 1) // 2) * 8),
+        "linesearch": n_roll * (T_HOR * (RXU + RLL + RXU) + RXU),
     }
     peak, peak_src = measured_peak_hbm()
     kernels = {}
@@ -319,10 +328,11 @@ def main():
     roofline = None
     if dom:
         a = kernels[dom]["achieved_gbs"]
-        roofline = {"kernel": "k_" + dom, "bound": "hbm", "achieved": a, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+        roofline = {"kernel": {"derivs": "k_derivs", "backpass": "k_backpass", "linesearch": "k_ls_round"}[dom], "bound": "hbm", "achieved": a, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                     "frac": a / peak if a else None, "traffic": traffic,
                     "algorithmic_bytes_per_launch": alg[dom] / kernels[dom]["launches"],
-                    "note": "lane-per-problem fp64 kernel: issue/latency-bound, far below the HBM roof by design; see DESIGN.md"}
+                    "timed_on": f"{n_k} problems (one chunk of the timed run), kernels alone on one stream",
+                    "note": "algorithmic bytes = record/entry bytes of DESIGN.md section 5 x units counted by the kernels"}
 
     # ---- CPU baseline on the host cores (rank 0, N = 1 only) -----------------------------------------------------------------
     cpu = None
@@ -347,6 +357,7 @@ def main():
                     "seconds": ms_e2e_max * 1e-3},
             "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
             "iterations_total": its_total, "seconds": ms_max * 1e-3, "deterministic_rerun": deterministic,
+            "streams_per_gpu": S.chunks(),
         }
         print(json.dumps(line))
     S.close()

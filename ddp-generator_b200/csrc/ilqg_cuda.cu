@@ -89,17 +89,17 @@ int ilqgk_launch_backpass(const ilqg_work *w, const ilqg_opts *o, const double *
     return check(cudaGetLastError(), "k_backpass");
 }
 
-int ilqgk_launch_linesearch(const ilqg_work *w, const ilqg_opts *o, const double *params, int iter, void *stream)
+/* line search = one launch per alpha; rounds > 0 read their problem list and count from device memory, so there is
+   no host round trip.  Their grids are sized for the worst case and surplus blocks exit at once. */
+int ilqgk_launch_ls_reset(const ilqg_work *w, void *stream)
 {
-    /* one launch per alpha; rounds > 0 read their problem list and count from device memory, so no host round trip.
-       Their grids are sized for the worst case and surplus blocks exit at once. */
-    if (check(cudaMemsetAsync(w->ls_count, 0, sizeof(int) * (ILQG_MAX_ALPHA + 2), (cudaStream_t)stream), "memset ls_count")) return -1;
-    const ParamBlock<P> pb = make_pb(params);
-    for (int r = 0; r < o->n_alpha; r++) {
-        k_ls_round<P><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, pb, iter, r);
-        if (check(cudaGetLastError(), "k_ls_round")) return -1;
-    }
-    return 0;
+    return check(cudaMemsetAsync(w->ls_count, 0, sizeof(int) * (ILQG_MAX_ALPHA + 2), (cudaStream_t)stream), "memset ls_count");
+}
+
+int ilqgk_launch_ls_round(const ilqg_work *w, const ilqg_opts *o, const double *params, int iter, int round, void *stream)
+{
+    k_ls_round<P><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, make_pb(params), iter, round);
+    return check(cudaGetLastError(), "k_ls_round");
 }
 
 int ilqgk_launch_post(const ilqg_work *w, const ilqg_opts *o, const double *params, void *stream)

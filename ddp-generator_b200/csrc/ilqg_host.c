@@ -496,10 +496,14 @@ static int launch_pass(chunk *h, int do_derivs, int do_back, int do_ls)
         timing_end(h, p);
     }
     if (do_ls) {
-        p = timing_begin(h, TC_LINESEARCH);
-        if (ilqgk_launch_linesearch(&h->w, &h->o, h->params, h->iter, h->stream)) return failk(h);
-        h->n_launches += h->o.n_alpha;
-        timing_end(h, p);
+        int r;
+        if (ilqgk_launch_ls_reset(&h->w, h->stream)) return failk(h);
+        for (r = 0; r < h->o.n_alpha; r++) {
+            p = timing_begin(h, TC_LINESEARCH);
+            if (ilqgk_launch_ls_round(&h->w, &h->o, h->params, h->iter, r, h->stream)) return failk(h);
+            h->n_launches++;
+            timing_end(h, p);
+        }
         if (ilqgk_has_post()) {
             p = timing_begin(h, TC_POST);
             if (ilqgk_launch_post(&h->w, &h->o, h->params, h->stream)) return failk(h);
