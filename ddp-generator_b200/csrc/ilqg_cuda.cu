@@ -70,10 +70,16 @@ int ilqgk_event_elapsed(void *a, void *b, float *ms) { return check(cudaEventEla
 
 static inline unsigned nblk(int n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
-int ilqgk_launch_init(const ilqg_work *w, const ilqg_opts *o, const double *params, void *stream)
+int ilqgk_launch_init(const ilqg_work *w, const ilqg_opts *o, const double *params, int mode, void *stream)
 {
-    k_init<P><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, make_pb(params));
+    k_init<P><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, make_pb(params), mode);
     return check(cudaGetLastError(), "k_init");
+}
+
+int ilqgk_launch_rollout(const ilqg_work *w, const double *params, double alpha, int cost_only, void *stream)
+{
+    k_rollout_only<P><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, make_pb(params), alpha, cost_only);
+    return check(cudaGetLastError(), "k_rollout_only");
 }
 
 int ilqgk_launch_derivs(const ilqg_work *w, const double *params, void *stream)
@@ -124,13 +130,13 @@ int ilqgk_launch_count_active(const ilqg_work *w, int *d_counter, void *stream)
     return check(cudaGetLastError(), "k_count_active");
 }
 
-int ilqgk_launch_scatter(const double *src, double *dst, int B, int n_k, int n_i, long long stride_k, long long stride_b,
-                         long long stride_i, long long off, void *stream)
+int ilqgk_launch_scatter(const double *src, double *dst, double *dst_alt, const int *sel, int B, int n_k, int n_i, long long stride_k,
+                         long long stride_b, long long stride_i, long long off, void *stream)
 {
     const size_t n = (size_t)B * n_k * n_i;
     if (!n) return 0;
     const Layout L = {stride_k, stride_b, stride_i, off};
-    k_scatter<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, dst, B, n_k, n_i, L);
+    k_scatter<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, dst, dst_alt, sel, B, n_k, n_i, L);
     return check(cudaGetLastError(), "k_scatter");
 }
 

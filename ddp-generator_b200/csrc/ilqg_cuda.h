@@ -38,7 +38,9 @@ int ilqgk_event_destroy(void *e);
 int ilqgk_event_record(void *e, void *s);
 int ilqgk_event_elapsed(void *a, void *b, float *ms);
 
-int ilqgk_launch_init(const ilqg_work *w, const ilqg_opts *o, const double *params, void *stream);
+/* mode bits: 1 init multipliers, 2 initial rollout of buffer 0 into buffer 1, 4 first lines of iLQG() */
+int ilqgk_launch_init(const ilqg_work *w, const ilqg_opts *o, const double *params, int mode, void *stream);
+int ilqgk_launch_rollout(const ilqg_work *w, const double *params, double alpha, int cost_only, void *stream);
 int ilqgk_launch_derivs(const ilqg_work *w, const double *params, void *stream);
 int ilqgk_launch_backpass(const ilqg_work *w, const ilqg_opts *o, const double *params, int iter, void *stream);
 int ilqgk_launch_ls_reset(const ilqg_work *w, void *stream);
@@ -48,8 +50,8 @@ int ilqgk_has_post(void);
 int ilqgk_launch_finalize(const ilqg_work *w, int max_iter, void *stream);
 int ilqgk_launch_count_active(const ilqg_work *w, int *d_counter, void *stream);
 /* [B][n_k][n_i] (host order) <-> device element (k, b, i) at base[k*stride_k + b*stride_b + i*stride_i + off] */
-int ilqgk_launch_scatter(const double *src, double *dst, int B, int n_k, int n_i, long long stride_k, long long stride_b,
-                         long long stride_i, long long off, void *stream);
+int ilqgk_launch_scatter(const double *src, double *dst, double *dst_alt, const int *sel, int B, int n_k, int n_i, long long stride_k,
+                         long long stride_b, long long stride_i, long long off, void *stream);
 int ilqgk_launch_gather(const double *src, const double *src_alt, const int *sel, double *dst, int B, int n_k, int n_i,
                         long long stride_k, long long stride_b, long long stride_i, long long off, void *stream);
 

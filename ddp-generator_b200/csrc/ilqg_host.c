@@ -83,6 +83,13 @@ int ilqgb_n_params(void) { return ilqgk_param_count(); }
 const char *ilqgb_param_name(int i) { return ilqgk_param_name(i); }
 int ilqgb_param_size(int i) { return ilqgk_param_size(i); }
 int ilqgb_device_count(void) { return ilqgk_device_count(); }
+void ilqgb_mult_counts(int *n_running_eq, int *n_final_eq)
+{
+    ilqgk_dims_t d;
+    ilqgk_dims(&d);
+    if (n_running_eq) *n_running_eq = d.n_mu_le;
+    if (n_final_eq) *n_final_eq = d.n_mu_fe;
+}
 int ilqgb_deriv_doubles_per_step(void) { ilqgk_dims_t d; ilqgk_dims(&d); return d.nv1 + (d.full_ddp ? d.nv2 : 0); }
 
 static void ck_destroy(chunk *h);
@@ -354,7 +361,8 @@ static int ensure_traces(chunk *h)
     h->w.tr_lambda = (double *)dalloc(h, sizeof(double) * n);
     h->w.tr_newcost = (double *)dalloc(h, sizeof(double) * n);
     h->w.tr_alpha = (int *)dalloc(h, sizeof(int) * n);
-    if (!h->w.tr_lambda || !h->w.tr_newcost || !h->w.tr_alpha) return -1;
+    h->w.tr_z = (double *)dalloc(h, sizeof(double) * n);
+    if (!h->w.tr_lambda || !h->w.tr_newcost || !h->w.tr_alpha || !h->w.tr_z) return -1;
     h->trace_cap = need;
     return 0;
 }
@@ -368,9 +376,9 @@ static int ck_upload(chunk *h, const double *x0, const double *u_nom)
     if (ilqgk_h2d(h->d_stage, u_nom, sizeof(double) * B * T * nu, h->stream)) return failk(h);
     if (ilqgk_h2d(h->d_stage + B * T * nu, x0, sizeof(double) * B * nx, h->stream)) return failk(h);
     /* controls into the u part of buffer 0's records; x0 into its own [NX][Bp] array */
-    if (ilqgk_launch_scatter(h->d_stage, h->w.XU[0], h->B, h->T, h->d.nu, (long long)h->Bp * h->d.rxu, h->d.rxu, 1, h->d.nx, h->stream)) return failk(h);
+    if (ilqgk_launch_scatter(h->d_stage, h->w.XU[0], NULL, NULL, h->B, h->T, h->d.nu, (long long)h->Bp * h->d.rxu, h->d.rxu, 1, h->d.nx, h->stream)) return failk(h);
     h->n_launches += 2;
-    if (ilqgk_launch_scatter(h->d_stage + B * T * nu, h->w.x0, h->B, 1, h->d.nx, 0, 1, h->Bp, 0, h->stream)) return failk(h);
+    if (ilqgk_launch_scatter(h->d_stage + B * T * nu, h->w.x0, NULL, NULL, h->B, 1, h->d.nx, 0, 1, h->Bp, 0, h->stream)) return failk(h);
     h->started = 0;
     return 0;
 }
@@ -473,7 +481,7 @@ static int ck_start(chunk *h)
         for (i = 0; i < 2; i++)
             if (ilqgk_memset(h->w.LL[i], 0, sizeof(double) * (size_t)h->T * h->Bp * h->d.rll, h->stream)) return failk(h);
     }
-    if (ilqgk_launch_init(&h->w, &h->o, h->params, h->stream)) return failk(h);
+    if (ilqgk_launch_init(&h->w, &h->o, h->params, 7, h->stream)) return failk(h);
     h->n_launches++;
     h->iter = 0;
     h->started = 1;
@@ -578,49 +586,87 @@ static int ck_phase_backpass(chunk *h) { return ilqgk_set_device(h->device) ? fa
 static int ck_phase_linesearch(chunk *h) { return ilqgk_set_device(h->device) ? failk(h) : launch_pass(h, 0, 0, 1); }
 
 /* ---- read-back -------------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    double *scal;             /* per-problem scalar array, or */
+    double *src, *alt;        /* trajectory-like field (alt = second buffer, chosen by sel) */
+    const int *sel;
+    int n_k, n_i;
+    lay_t L;
+} field_t;
+
+static int find_field(chunk *h, const char *f, field_t *o)
+{
+    ilqg_work *w = &h->w;
+    const ilqgk_dims_t *d = &h->d;
+    memset(o, 0, sizeof *o);
+    if (!strcmp(f, "cost")) o->scal = w->cost;
+    else if (!strcmp(f, "new_cost")) o->scal = w->new_cost;
+    else if (!strcmp(f, "dcost")) o->scal = w->dcost;
+    else if (!strcmp(f, "expected")) o->scal = w->expected;
+    else if (!strcmp(f, "lambda")) o->scal = w->lambda;
+    else if (!strcmp(f, "dlambda")) o->scal = w->dlambda;
+    else if (!strcmp(f, "g_norm")) o->scal = w->g_norm;
+    else if (!strcmp(f, "dV0")) o->scal = w->dV0;
+    else if (!strcmp(f, "dV1")) o->scal = w->dV1;
+    else if (!strcmp(f, "w_pen_l")) o->scal = w->w_pen_l;
+    else if (!strcmp(f, "w_pen_f")) o->scal = w->w_pen_f;
+    if (o->scal) return 0;
+    if (!strcmp(f, "x")) { o->src = w->XU[0]; o->alt = w->XU[1]; o->sel = w->cur; o->n_k = h->T + 1; o->n_i = d->nx; o->L = lay_rec(h, d->rxu, 0); }
+    else if (!strcmp(f, "u")) { o->src = w->XU[0]; o->alt = w->XU[1]; o->sel = w->cur; o->n_k = h->T; o->n_i = d->nu; o->L = lay_rec(h, d->rxu, d->nx); }
+    else if (!strcmp(f, "x_cand")) { o->src = w->XU[1]; o->alt = w->XU[0]; o->sel = w->cur; o->n_k = h->T + 1; o->n_i = d->nx; o->L = lay_rec(h, d->rxu, 0); }
+    else if (!strcmp(f, "u_cand")) { o->src = w->XU[1]; o->alt = w->XU[0]; o->sel = w->cur; o->n_k = h->T; o->n_i = d->nu; o->L = lay_rec(h, d->rxu, d->nx); }
+    else if (!strcmp(f, "x0")) { o->src = w->x0; o->n_k = 1; o->n_i = d->nx; o->L = lay_soa(h, d->nx); }
+    else if (!strcmp(f, "l")) { o->src = w->LL[0]; o->alt = w->LL[1]; o->sel = w->cur; o->n_k = h->T; o->n_i = d->nu; o->L = lay_rec(h, d->rll, 0); }
+    else if (!strcmp(f, "L")) { o->src = w->LL[0]; o->alt = w->LL[1]; o->sel = w->cur; o->n_k = h->T; o->n_i = d->nu * d->nx; o->L = lay_rec(h, d->rll, d->nu); }
+    else if (!strcmp(f, "v1")) { o->src = w->V1; o->n_k = h->T; o->n_i = d->nv1; o->L = lay_soa(h, o->n_i); }
+    else if (!strcmp(f, "v2") && d->full_ddp) { o->src = w->V2; o->n_k = h->T; o->n_i = d->nv2; o->L = lay_soa(h, o->n_i); }
+    else if (!strcmp(f, "fd")) { o->src = w->FD; o->n_k = 1; o->n_i = d->nx + d->nqxx; o->L = lay_soa(h, o->n_i); }
+    else if (!strcmp(f, "mu_f")) { o->src = w->muF; o->n_k = 1; o->n_i = d->n_mu_f; o->L = lay_soa(h, o->n_i); }
+    else if (!strcmp(f, "last_f")) { o->src = w->lastF; o->n_k = 1; o->n_i = d->n_mu_f; o->L = lay_soa(h, o->n_i); }
+    else if (!strcmp(f, "mu_r")) { o->src = w->muR; o->n_k = h->T; o->n_i = d->n_mu_r; o->L = lay_soa(h, o->n_i); }
+    else if (!strcmp(f, "last_r")) { o->src = w->lastR; o->n_k = h->T; o->n_i = d->n_mu_r; o->L = lay_soa(h, o->n_i); }
+    else if (!strcmp(f, "tr_lambda") && w->tr_lambda) { o->src = w->tr_lambda; o->n_k = h->trace_cap; o->n_i = 1; o->L = lay_soa(h, 1); }
+    else if (!strcmp(f, "tr_newcost") && w->tr_newcost) { o->src = w->tr_newcost; o->n_k = h->trace_cap; o->n_i = 1; o->L = lay_soa(h, 1); }
+    else if (!strcmp(f, "tr_z") && w->tr_z) { o->src = w->tr_z; o->n_k = h->trace_cap; o->n_i = 1; o->L = lay_soa(h, 1); }
+    else return fail(h, "unknown field");
+    return 0;
+}
+
 static long ck_get(chunk *h, const char *f, double *out)
 {
-    const ilqg_work *w = &h->w;
-    const ilqgk_dims_t *d = &h->d;
     const size_t B = (size_t)h->B;
-    const double *scal = NULL;
+    field_t fd;
     if (ilqgk_set_device(h->device)) return failk(h);
-    if (!strcmp(f, "cost")) scal = w->cost;
-    else if (!strcmp(f, "new_cost")) scal = w->new_cost;
-    else if (!strcmp(f, "dcost")) scal = w->dcost;
-    else if (!strcmp(f, "expected")) scal = w->expected;
-    else if (!strcmp(f, "lambda")) scal = w->lambda;
-    else if (!strcmp(f, "dlambda")) scal = w->dlambda;
-    else if (!strcmp(f, "g_norm")) scal = w->g_norm;
-    else if (!strcmp(f, "dV0")) scal = w->dV0;
-    else if (!strcmp(f, "dV1")) scal = w->dV1;
-    else if (!strcmp(f, "w_pen_l")) scal = w->w_pen_l;
-    else if (!strcmp(f, "w_pen_f")) scal = w->w_pen_f;
-    if (scal) {
-        if (ilqgk_d2h(out, scal, sizeof(double) * B, h->stream) || ilqgk_stream_sync(h->stream)) return failk(h);
+    if (find_field(h, f, &fd)) return -1;
+    if (fd.scal) {
+        if (ilqgk_d2h(out, fd.scal, sizeof(double) * B, h->stream) || ilqgk_stream_sync(h->stream)) return failk(h);
         return (long)B;
     }
-    {
-        const double *src = NULL, *alt = NULL;
-        const int *sel = NULL;
-        int n_k = 0, n_i = 0;
-        lay_t L;
-        if (!strcmp(f, "x")) { src = w->XU[0]; alt = w->XU[1]; sel = w->cur; n_k = h->T + 1; n_i = d->nx; L = lay_rec(h, d->rxu, 0); }
-        else if (!strcmp(f, "u")) { src = w->XU[0]; alt = w->XU[1]; sel = w->cur; n_k = h->T; n_i = d->nu; L = lay_rec(h, d->rxu, d->nx); }
-        else if (!strcmp(f, "l")) { src = w->LL[0]; alt = w->LL[1]; sel = w->cur; n_k = h->T; n_i = d->nu; L = lay_rec(h, d->rll, 0); }
-        else if (!strcmp(f, "L")) { src = w->LL[0]; alt = w->LL[1]; sel = w->cur; n_k = h->T; n_i = d->nu * d->nx; L = lay_rec(h, d->rll, d->nu); }
-        else if (!strcmp(f, "v1")) { src = w->V1; n_k = h->T; n_i = d->nv1; L = lay_soa(h, n_i); }
-        else if (!strcmp(f, "v2") && d->full_ddp) { src = w->V2; n_k = h->T; n_i = d->nv2; L = lay_soa(h, n_i); }
-        else if (!strcmp(f, "fd")) { src = w->FD; n_k = 1; n_i = d->nx + d->nqxx; L = lay_soa(h, n_i); }
-        else if (!strcmp(f, "mu_f")) { src = w->muF; n_k = 1; n_i = d->n_mu_f; L = lay_soa(h, n_i); }
-        else if (!strcmp(f, "mu_r")) { src = w->muR; n_k = h->T; n_i = d->n_mu_r; L = lay_soa(h, n_i); }
-        else if (!strcmp(f, "tr_lambda") && w->tr_lambda) { src = w->tr_lambda; n_k = h->trace_cap; n_i = 1; L = lay_soa(h, 1); }
-        else if (!strcmp(f, "tr_newcost") && w->tr_newcost) { src = w->tr_newcost; n_k = h->trace_cap; n_i = 1; L = lay_soa(h, 1); }
-        else return fail(h, "unknown field");
-        if (gather_to_host(h, src, alt, sel, n_k, n_i, L, out)) return -1;
-        if (ilqgk_stream_sync(h->stream)) return failk(h);
-        return (long)(B * n_k * n_i);
+    if (gather_to_host(h, fd.src, fd.alt, fd.sel, fd.n_k, fd.n_i, fd.L, out)) return -1;
+    if (ilqgk_stream_sync(h->stream)) return failk(h);
+    return (long)(B * fd.n_k * fd.n_i);
+}
+
+/* host -> device write of one field (same names and shapes as ck_get) */
+static long ck_put(chunk *h, const char *f, const double *in)
+{
+    const size_t B = (size_t)h->B;
+    field_t fd;
+    size_t n;
+    if (ilqgk_set_device(h->device)) return failk(h);
+    if (find_field(h, f, &fd)) return -1;
+    if (fd.scal) {
+        if (ilqgk_h2d(fd.scal, in, sizeof(double) * B, h->stream) || ilqgk_stream_sync(h->stream)) return failk(h);
+        return (long)B;
     }
+    n = B * fd.n_k * fd.n_i;
+    if (!n) return 0;
+    if (ensure_stage(h, n)) return -1;
+    if (ilqgk_h2d(h->d_stage, in, sizeof(double) * n, h->stream)) return failk(h);
+    if (ilqgk_launch_scatter(h->d_stage, fd.src, fd.alt, fd.sel, h->B, fd.n_k, fd.n_i, fd.L.stride_k, fd.L.stride_b, fd.L.stride_i, fd.L.off, h->stream)) return failk(h);
+    h->n_launches++;
+    if (ilqgk_stream_sync(h->stream)) return failk(h);
+    return (long)n;
 }
 
 static long ck_get_int(chunk *h, const char *f, int *out)
@@ -660,6 +706,39 @@ static long ck_get_int(chunk *h, const char *f, int *out)
     }
 }
 
+
+static long ck_put_int(chunk *h, const char *f, const int *in)
+{
+    const size_t B = (size_t)h->B;
+    int *dst = NULL;
+    if (ilqgk_set_device(h->device)) return failk(h);
+    if (!strcmp(f, "cur")) dst = h->w.cur;
+    else if (!strcmp(f, "status")) dst = h->w.status;
+    else return fail(h, "unknown field");
+    if (ilqgk_h2d(dst, in, sizeof(int) * B, h->stream) || ilqgk_stream_sync(h->stream)) return failk(h);
+    return (long)B;
+}
+
+/* start of a solve on imported state (nominal trajectory, cost, multipliers already on the device): only the first
+   lines of iLQG() run (iLQG.c:226-237) -- used by the single-problem drop-in iLQG(tOptSet*) */
+static int ck_begin(chunk *h)
+{
+    if (ilqgk_set_device(h->device)) return failk(h);
+    if (ensure_traces(h)) return -1;
+    if (ilqgk_launch_init(&h->w, &h->o, h->params, 4, h->stream)) return failk(h);
+    h->n_launches++;
+    h->iter = 0;
+    h->started = 1;
+    return 0;
+}
+
+static int ck_rollout(chunk *h, double alpha, int cost_only)
+{
+    if (ilqgk_set_device(h->device)) return failk(h);
+    if (ilqgk_launch_rollout(&h->w, h->params, alpha, cost_only, h->stream)) return failk(h);
+    h->n_launches++;
+    return 0;
+}
 
 /* =====================================================================================================================
  * Public handle: the batch is split into contiguous chunks, each a complete single-stream solver (above) on its own
@@ -961,3 +1040,49 @@ long ilqgb_launch_count(const ilqgb_handle *h)
 }
 
 int ilqgb_chunks(const ilqgb_handle *h) { return h->n; }
+
+
+long ilqgb_put(ilqgb_handle *h, const char *field, const double *in)
+{
+    int i;
+    long per = -1, tot = 0;
+    if (ilqgb_sync(h)) return -1;
+    for (i = 0; i < h->n; i++) {
+        long n = ck_put(h->c[i], field, in + (per < 0 ? 0 : (size_t)h->first[i] * per));
+        if (n < 0) return hfail(h, h->c[i]);
+        if (per < 0) per = n / h->c[i]->B;
+        tot += n;
+    }
+    return tot;
+}
+
+long ilqgb_put_int(ilqgb_handle *h, const char *field, const int *in)
+{
+    int i;
+    long tot = 0;
+    if (ilqgb_sync(h)) return -1;
+    for (i = 0; i < h->n; i++) {
+        long n = ck_put_int(h->c[i], field, in + h->first[i]);
+        if (n < 0) return hfail(h, h->c[i]);
+        tot += n;
+    }
+    return tot;
+}
+
+int ilqgb_begin(ilqgb_handle *h)
+{
+    int i;
+    if (fork_streams(h)) return -1;
+    for (i = 0; i < h->n; i++)
+        if (ck_begin(h->c[i])) return hfail(h, h->c[i]);
+    return join_streams(h);
+}
+
+int ilqgb_rollout(ilqgb_handle *h, double alpha, int cost_only)
+{
+    int i;
+    if (fork_streams(h)) return -1;
+    for (i = 0; i < h->n; i++)
+        if (ck_rollout(h->c[i], alpha, cost_only)) return hfail(h, h->c[i]);
+    return join_streams(h);
+}

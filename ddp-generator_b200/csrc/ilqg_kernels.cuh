@@ -773,33 +773,41 @@ __device__ __forceinline__ bool cost_pass(const Work &w, const ParamBlock<P> &pb
     return true;
 }
 
+enum { INIT_MULT = 1, INIT_ROLLOUT = 2, INIT_BEGIN = 4, INIT_ALL = 7 };
+
 template <class P>
-__global__ void __launch_bounds__(BP_BLOCK) k_init(Work w, Opts o, ParamBlock<P> pb)
+__global__ void __launch_bounds__(BP_BLOCK) k_init(Work w, Opts o, ParamBlock<P> pb, int mode)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= w.B) return;
     const size_t Bp = w.Bp;
     const int T = w.T;
-    /* init_multipliers (iLQG_func.tem:364-400) */
-    for (int k = 0; k < T; k++)
+    if (mode & INIT_MULT) { /* init_multipliers (iLQG_func.tem:364-400) */
+        for (int k = 0; k < T; k++)
 #pragma unroll
-        for (int i = 0; i < P::N_MU_R; i++) {
-            w.muR[((size_t)k * P::N_MU_R + i) * Bp + b] = (i < P::N_MU_LE) ? 0.0 : 1.0;
-            w.lastR[((size_t)k * P::N_MU_R + i) * Bp + b] = 0.0;
+            for (int i = 0; i < P::N_MU_R; i++) {
+                w.muR[((size_t)k * P::N_MU_R + i) * Bp + b] = (i < P::N_MU_LE) ? 0.0 : 1.0;
+                w.lastR[((size_t)k * P::N_MU_R + i) * Bp + b] = 0.0;
+            }
+#pragma unroll
+        for (int i = 0; i < P::N_MU_F; i++) {
+            w.muF[(size_t)i * Bp + b] = (i < P::N_MU_FE) ? 0.0 : 1.0;
+            w.lastF[(size_t)i * Bp + b] = 0.0;
         }
-#pragma unroll
-    for (int i = 0; i < P::N_MU_F; i++) {
-        w.muF[(size_t)i * Bp + b] = (i < P::N_MU_FE) ? 0.0 : 1.0;
-        w.lastF[(size_t)i * Bp + b] = 0.0;
     }
     /* the caller's controls sit in buffer 0; roll them out (clamped) into buffer 1, which becomes nominal.
        The harness-level rollout runs before iLQG() sets the penalty weights, i.e. with whatever the option struct
        holds: w_pen_l/f are still their zero-initialised values at that point (iLQG_mex.c:24,116). */
-    double csum;
-    const bool ok = rollout<P>(w, pb, b, 0, 1, 0.0, 0.0, 0.0, csum);
-    w.cur[b] = 1;
-    w.cost[b] = csum;
-    w.new_cost[b] = csum;
+    bool ok = true;
+    if (mode & INIT_ROLLOUT) {
+        double csum;
+        ok = rollout<P>(w, pb, b, 0, 1, 0.0, 0.0, 0.0, csum);
+        w.cur[b] = 1;
+        w.cost[b] = csum;
+        w.new_cost[b] = csum;
+    }
+    if (!(mode & INIT_BEGIN)) return;
+    const int nb = w.cur[b]; /* nominal buffer */
     w.dcost[b] = 0.0;
     w.expected[b] = 0.0;
     w.g_norm[b] = 0.0;
@@ -828,7 +836,7 @@ __global__ void __launch_bounds__(BP_BLOCK) k_init(Work w, Opts o, ParamBlock<P>
             mun[P::N_MU_R + P::N_MU_F + 1];
         if (P::N_MU_R > 0 && T > 0) {
             double xu[Rec<P>::RXU];
-            ld_rec<P::NX + P::NU>(w.XU[1] + (size_t)b * Rec<P>::RXU, xu);
+            ld_rec<P::NX + P::NU>(w.XU[nb] + (size_t)b * Rec<P>::RXU, xu);
 #pragma unroll
             for (int i = 0; i < P::NX; i++) x[i] = xu[i];
 #pragma unroll
@@ -840,7 +848,7 @@ __global__ void __launch_bounds__(BP_BLOCK) k_init(Work w, Opts o, ParamBlock<P>
             for (int i = 0; i < P::N_MU_R; i++) w.lastR[(size_t)i * Bp + b] = hval[i];
         }
         if (P::N_MU_F > 0) {
-            ld_rec<P::NX>(w.XU[1] + ((size_t)T * Bp + b) * Rec<P>::RXU, x);
+            ld_rec<P::NX>(w.XU[nb] + ((size_t)T * Bp + b) * Rec<P>::RXU, x);
 #pragma unroll
             for (int i = 0; i < P::N_MU_F; i++) mu[i] = w.muF[(size_t)i * Bp + b];
             P::mult_final(x, pb.v, w.pk, T, T, o.w_pen_init_f, mu, hval, mun);
@@ -848,6 +856,22 @@ __global__ void __launch_bounds__(BP_BLOCK) k_init(Work w, Opts o, ParamBlock<P>
             for (int i = 0; i < P::N_MU_F; i++) w.lastF[(size_t)i * Bp + b] = hval[i];
         }
     }
+}
+
+/* forward_pass(candidate, o, alpha, &csum, cost_only) of the single-problem API on its own (iLQG_func.tem:121-185):
+ * one rollout from the nominal buffer into the other one (or the cost-only pass over the nominal); csum -> new_cost,
+ * success flag -> result.  No solver bookkeeping. */
+template <class P>
+__global__ void __launch_bounds__(BP_BLOCK) k_rollout_only(Work w, ParamBlock<P> pb, double alpha, int cost_only)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= w.B) return;
+    const int cur = w.cur[b];
+    double csum;
+    const bool ok = cost_only ? cost_pass<P>(w, pb, b, cur, w.w_pen_l[b], w.w_pen_f[b], csum)
+                              : rollout<P>(w, pb, b, cur, cur ^ 1, alpha, w.w_pen_l[b], w.w_pen_f[b], csum);
+    w.new_cost[b] = csum;
+    w.result[b] = ok ? 1 : 0;
 }
 
 /* K3: line search, one ROUND per launch.  Round r rolls out alpha[r] for every problem that has not accepted a step
@@ -888,6 +912,7 @@ k_ls_round(Work w, Opts o, ParamBlock<P> pb, int iter, int round)
             expected = -alpha * (dV0 + alpha * dV1);
             const double z = (expected > 0) ? dcost / expected : 0.0;
             accepted = z > o.zMin;
+            if (w.tr_z) w.tr_z[(size_t)iter * Bp + b] = z;
         }
         w.new_cost[b] = cnew;
         w.dcost[b] = dcost;
@@ -1042,13 +1067,14 @@ struct Layout {
     long long stride_k, stride_b, stride_i, off;
 };
 
-__global__ void k_scatter(const double *src, double *dst, int B, int n_k, int n_i, Layout L)
+__global__ void k_scatter(const double *src, double *dst, double *dst_alt, const int *sel, int B, int n_k, int n_i, Layout L)
 {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t per = (size_t)n_k * n_i;
     if (e >= per * B) return;
     const size_t i = e % n_i, b = (e / n_i) % B, k = e / ((size_t)n_i * B);
-    dst[k * L.stride_k + b * L.stride_b + i * L.stride_i + L.off] = src[b * per + k * n_i + i];
+    double *d = (sel && sel[b]) ? dst_alt : dst;
+    d[k * L.stride_k + b * L.stride_b + i * L.stride_i + L.off] = src[b * per + k * n_i + i];
 }
 
 __global__ void k_gather(const double *src, const double *src_alt, const int *sel, double *dst, int B, int n_k, int n_i, Layout L)

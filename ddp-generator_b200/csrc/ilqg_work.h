@@ -30,7 +30,7 @@ typedef struct ilqg_work {
     int *ls_list[2], *ls_count; /* line search: compacted lists of undecided problems (ping-pong), per-round counts */
     int *n_dv, *n_roll;        /* work counters: derivative sweeps consumed, rollouts tried (bench roofline accounting) */
     /* optional traces for parity tests (null when disabled) */
-    double *tr_lambda, *tr_newcost; /* [max_iter][Bp] */
+    double *tr_lambda, *tr_newcost, *tr_z; /* [max_iter][Bp]: lambda at the line search, last rollout cost, last z */
     int *tr_alpha;                  /* [max_iter][Bp] */
     int *tr_clamp;                  /* [T][Bp]: is_clamped of the last back pass, 2 bits per input, QP code << 16 */
 } ilqg_work;

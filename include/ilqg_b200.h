@@ -46,6 +46,7 @@ int ilqgb_n_params(void);
 const char *ilqgb_param_name(int i);
 int ilqgb_param_size(int i); /* 1, k > 1, or -1: one value per timestep (n_hor + 1) */
 int ilqgb_device_count(void);
+void ilqgb_mult_counts(int *n_running_eq, int *n_final_eq); /* equality constraints among the running / final multipliers */
 int ilqgb_deriv_doubles_per_step(void); /* time-varying derivative doubles the derivative kernel stores per step */
 
 /* lifecycle; `stream` may be NULL (the handle then owns a stream) or a cudaStream_t of the caller */
@@ -87,6 +88,15 @@ long ilqgb_get(ilqgb_handle *h, const char *field, double *out);
 /* "iterations" "result" "status" "n_linesearch" "n_backpass" "n_derivs" "n_rollouts" "cur" -> [batch]; "tr_alpha" -> [batch][max_iter];
  * "tr_clamp" -> [batch][n_hor] (2 bits per input: 0 free, 1 lower, 2 upper; QP return code in bits 16..23) */
 long ilqgb_get_int(ilqgb_handle *h, const char *field, int *out);
+
+/* host -> device write of a field (names and shapes of ilqgb_get, plus "x0" "x_cand" "u_cand" "last_r" "last_f";
+ * ints: "cur" "status"), a solve start on imported state (only the first lines of iLQG(), iLQG.c:226-237, run), and a
+ * bare rollout = forward_pass(candidates[0] or nominal, o, alpha, &csum, cost_only) of iLQG.h:82: csum -> "new_cost",
+ * its return value -> "result".  These carry the single-problem drop-in (csrc/ilqg_dropin.c). */
+long ilqgb_put(ilqgb_handle *h, const char *field, const double *in);
+long ilqgb_put_int(ilqgb_handle *h, const char *field, const int *in);
+int ilqgb_begin(ilqgb_handle *h);
+int ilqgb_rollout(ilqgb_handle *h, double alpha, int cost_only);
 
 /* accumulated device time per kernel class since the last reset (ILQGB_TIMING): ms[4] / launches[4] in the
  * order derivs, backpass, linesearch, post */

@@ -11,9 +11,11 @@
 #include <pthread.h>
 
 #include "iLQG.h"
+#ifndef H_NO_PHASES
 #include "line_search.h"
 #include "back_pass.h"
 #include "boxQP.h"
+#endif
 #include "harness.h"
 
 #ifndef H_KIND
@@ -77,6 +79,7 @@ HSolver *h_create(int n_hor)
     standard_parameters(&s->o);
     s->o.debug_level = 0;
     s->max_iter_cap = 0;
+    s->o.w_pen_l = s->o.w_pen_f = 0.0;
     return s;
 }
 
@@ -133,6 +136,7 @@ int h_init(HSolver *s, const double *x0, const double *u0)
     g_cur = s;
     memcpy(s->x0, x0, sizeof(double) * N_X);
     s->n_ls = s->n_bp = s->n_qp = 0;
+    s->o.w_pen_l = s->o.w_pen_f = 0.0; /* a fresh INIT_OPTSET per call, as in the mex gateway (iLQG_mex.c:24) */
     ensure_logs(s);
     if (!init_opt(&s->o)) return 0;
     for (k = 0; k < s->n_hor; k++)
@@ -150,17 +154,23 @@ int h_solve(HSolver *s)
     return iLQG(&s->o);
 }
 
+#ifndef H_NO_PHASES
 int h_calc_derivs(HSolver *s) { g_cur = s; return calc_derivs(&s->o); }
 int h_back_pass(HSolver *s) { g_cur = s; return back_pass(&s->o); }
 int h_line_search(HSolver *s, int iter) { g_cur = s; ensure_logs(s); return line_search(&s->o, iter); }
+int h_update_multipliers(HSolver *s, int init) { return update_multipliers(&s->o, init); }
+#else /* a library that only exports the entry points the reference's mex gateway binds */
+int h_calc_derivs(HSolver *s) { (void)s; return -1; }
+int h_back_pass(HSolver *s) { (void)s; return -1; }
+int h_line_search(HSolver *s, int iter) { (void)s; (void)iter; return -1; }
+int h_update_multipliers(HSolver *s, int init) { (void)s; (void)init; return -1; }
+#endif
 int h_forward_pass(HSolver *s, double alpha, double *csum, int cost_only)
 {
     g_cur = s;
     return forward_pass(cost_only ? s->o.nominal : s->o.candidates[0], &s->o, alpha, csum, cost_only);
 }
 void h_make_candidate_nominal(HSolver *s) { makeCandidateNominal(&s->o, 0); }
-int h_update_multipliers(HSolver *s, int init) { return update_multipliers(&s->o, init); }
-
 void h_set_scalar(HSolver *s, const char *name, double v)
 {
     tOptSet *o = &s->o;
@@ -255,6 +265,7 @@ int h_get(HSolver *s, const char *field, double *out)
     return -1;
 }
 
+#ifndef H_NO_PHASES
 /* ---- spies ------------------------------------------------------------------------------------------------ */
 int h_spy_line_search(tOptSet *o, int iter)
 {
@@ -310,6 +321,8 @@ int h_spy_boxQP(double *H, const double *g, const double *lower, const double *u
     }
     return res;
 }
+
+#endif
 
 static const char *LS_NAMES[LS_FIELDS] = {"lambda", "g_norm", "dV0", "dV1", "cost", "success", "new_cost",
                                           "dcost", "expected", "alpha_idx", "iter"};

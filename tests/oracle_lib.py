@@ -13,7 +13,7 @@ _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 def lib_path(kind, problem, full_ddp, fast=False):
     d = "_ref" if kind == "reference" else "_build"
-    stem = "libref" if kind == "reference" else "libport"
+    stem = {"reference": "libref", "port": "libport", "b200": "libb200h"}[kind]   # b200 = harness over the GPU drop-in library
     return os.path.join(ROOT, "oracle", d, f"{stem}_{problem}_ddp{int(full_ddp)}{'_fast' if fast else ''}.so")
 
 
