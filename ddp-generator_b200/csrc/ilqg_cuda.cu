@@ -42,7 +42,7 @@ void ilqgk_dims(ilqgk_dims_t *d)
     d->nv1 = P::NV1; d->nv2 = P::NV2; d->npf = P::NPF_USED; d->nkp = P::NKP;
     d->n_mu_r = P::N_MU_R; d->n_mu_f = P::N_MU_F; d->n_mu_le = P::N_MU_LE; d->n_mu_fe = P::N_MU_FE;
     d->full_ddp = FULL_DDP; d->has_hx = P::HAS_HX ? 1 : 0;
-    d->rxu = Rec<P>::RXU; d->rll = Rec<P>::RLL;
+    d->rxu = Rec<P>::RXU; d->rll = Rec<P>::RLL; d->coop = use_coop<P>() ? 1 : 0;
 }
 const char *ilqgk_problem_name(void) { return P::name(); }
 int ilqgk_param_count(void) { return P::param_count(); }
@@ -91,7 +91,10 @@ int ilqgk_launch_derivs(const ilqg_work *w, const double *params, void *stream)
 
 int ilqgk_launch_backpass(const ilqg_work *w, const ilqg_opts *o, const double *params, int iter, void *stream)
 {
-    k_backpass<P, FULL_DDP != 0><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, make_pb(params), iter);
+    if constexpr (use_coop<P>())
+        k_backpass_warp<P, FULL_DDP != 0><<<nblk(w->B, CW_WARPS), CW_WARPS * 32, 0, (cudaStream_t)stream>>>(*w, *o, make_pb(params), iter);
+    else
+        k_backpass<P, FULL_DDP != 0><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, make_pb(params), iter);
     return check(cudaGetLastError(), "k_backpass");
 }
 

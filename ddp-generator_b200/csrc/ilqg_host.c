@@ -618,8 +618,8 @@ static int find_field(chunk *h, const char *f, field_t *o)
     else if (!strcmp(f, "x0")) { o->src = w->x0; o->n_k = 1; o->n_i = d->nx; o->L = lay_soa(h, d->nx); }
     else if (!strcmp(f, "l")) { o->src = w->LL[0]; o->alt = w->LL[1]; o->sel = w->cur; o->n_k = h->T; o->n_i = d->nu; o->L = lay_rec(h, d->rll, 0); }
     else if (!strcmp(f, "L")) { o->src = w->LL[0]; o->alt = w->LL[1]; o->sel = w->cur; o->n_k = h->T; o->n_i = d->nu * d->nx; o->L = lay_rec(h, d->rll, d->nu); }
-    else if (!strcmp(f, "v1")) { o->src = w->V1; o->n_k = h->T; o->n_i = d->nv1; o->L = lay_soa(h, o->n_i); }
-    else if (!strcmp(f, "v2") && d->full_ddp) { o->src = w->V2; o->n_k = h->T; o->n_i = d->nv2; o->L = lay_soa(h, o->n_i); }
+    else if (!strcmp(f, "v1")) { o->src = w->V1; o->n_k = h->T; o->n_i = d->nv1; o->L = d->coop ? lay_rec(h, d->nv1, 0) : lay_soa(h, o->n_i); }
+    else if (!strcmp(f, "v2") && d->full_ddp) { o->src = w->V2; o->n_k = h->T; o->n_i = d->nv2; o->L = d->coop ? lay_rec(h, d->nv2, 0) : lay_soa(h, o->n_i); }
     else if (!strcmp(f, "fd")) { o->src = w->FD; o->n_k = 1; o->n_i = d->nx + d->nqxx; o->L = lay_soa(h, o->n_i); }
     else if (!strcmp(f, "mu_f")) { o->src = w->muF; o->n_k = 1; o->n_i = d->n_mu_f; o->L = lay_soa(h, o->n_i); }
     else if (!strcmp(f, "last_f")) { o->src = w->lastF; o->n_k = 1; o->n_i = d->n_mu_f; o->L = lay_soa(h, o->n_i); }

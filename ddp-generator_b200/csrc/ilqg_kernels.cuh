@@ -47,6 +47,12 @@ using Work = ilqg_work;
 
 template <class P> struct ParamBlock { double v[P::NPF]; };
 
+#ifndef ILQG_FORCE_COOP
+#define ILQG_FORCE_COOP 0
+#endif
+/* problems whose backward-pass state does not fit one lane's registers use the warp-cooperative kernel */
+template <class P> __host__ __device__ constexpr bool use_coop() { return P::COOP || ILQG_FORCE_COOP; }
+
 __device__ __forceinline__ double dmax(double a, double b) { return (a > b) ? a : b; }
 __device__ __forceinline__ double dmin(double a, double b) { return (a < b) ? a : b; }
 __host__ __device__ constexpr int utri(int r, int c) { return (c * (c + 1)) / 2 + r; }
@@ -395,13 +401,24 @@ __global__ void __launch_bounds__(DV_BLOCK) k_derivs(Work w, ParamBlock<P> pb)
             ok = P::derivs_full(x, u, pb.v, w.pk, k, w.T, w_pen, mu, v1, v2);
         else
             ok = P::derivs(x, u, pb.v, w.pk, k, w.T, w_pen, mu, v1, v2);
-        double *o1 = w.V1 + (size_t)k * P::NV1 * Bp + b;
+        if (use_coop<P>()) { /* one contiguous record per (step, problem): the consumer is a whole warp per problem */
+            double *o1 = w.V1 + ((size_t)k * Bp + b) * P::NV1;
 #pragma unroll
-        for (int i = 0; i < P::NV1; i++) o1[i * Bp] = v1[i];
-        if (FULL) {
-            double *o2 = w.V2 + (size_t)k * P::NV2 * Bp + b;
+            for (int i = 0; i < P::NV1; i++) o1[i] = v1[i];
+            if (FULL) {
+                double *o2 = w.V2 + ((size_t)k * Bp + b) * P::NV2;
 #pragma unroll
-            for (int i = 0; i < P::NV2_USED; i++) o2[i * Bp] = v2[i];
+                for (int i = 0; i < P::NV2_USED; i++) o2[i] = v2[i];
+            }
+        } else {
+            double *o1 = w.V1 + (size_t)k * P::NV1 * Bp + b;
+#pragma unroll
+            for (int i = 0; i < P::NV1; i++) o1[i * Bp] = v1[i];
+            if (FULL) {
+                double *o2 = w.V2 + (size_t)k * P::NV2 * Bp + b;
+#pragma unroll
+                for (int i = 0; i < P::NV2_USED; i++) o2[i * Bp] = v2[i];
+            }
         }
     } else {
 #pragma unroll
@@ -680,6 +697,361 @@ __global__ void __launch_bounds__(BP_BLOCK, ILQG_BP_MINBLOCKS) k_backpass(Work w
         w.g_norm[b] = g_norm;
     }
     if (g_norm < o.tolGrad && lambda < 1e-5) { /* iLQG.c:297-303 */
+        lower_lambda(o, lambda, dlambda);
+        finish(w, b, iter, done ? 1 : 0);
+    } else if (!done) {
+        finish(w, b, iter, 0);
+    }
+    w.lambda[b] = lambda;
+    w.dlambda[b] = dlambda;
+}
+
+/* =====================================================================================================================
+ * K2w: backward pass, one WARP per problem (larger state dimensions: the quadrotor has Vxx 78, Qxx 78, fx 144 ...
+ * doubles per step).  All matrices live in shared memory; a lane owns OUTPUT ELEMENTS and evaluates each of its dot
+ * products serially in the reference's summation order -- there is no cross-lane reduction anywhere, so results are
+ * bit-identical to the lane-per-problem kernel and to the reference.  The m x m box-QP runs redundantly in every
+ * lane's registers (uniform control flow, no broadcast needed).  The FULL_DDP tensor contractions are data-driven
+ * sparse term lists emitted by the generator.
+ * ===================================================================================================================== */
+constexpr int CW_WARPS = 4;
+
+template <class P> struct CoopWS {
+    Dense<P> D;
+    double Vx[P::NX], Vxx[P::NQXX], Qx[P::NX], Qu[P::NU], Qxx[P::NQXX], Quu[P::NQUU], Qxu[P::NQXU], QuuF[P::NQUU], Qxu_reg[P::NQXU];
+    double ba[P::NX * P::NX], bc[P::NX * P::NU], bl[P::NU * P::NX], bv[P::NU];
+    double Lk[P::NU * P::NX], lk[P::NU], invH[P::NQUU];
+    double v2[P::NV2], c2[P::NC2];
+    int clamped[P::NU];
+};
+
+__device__ __forceinline__ void tri_rc(int e, int &r, int &c)
+{
+    c = 0;
+    while (((c + 1) * (c + 2)) / 2 <= e) c++;
+    r = e - (c * (c + 1)) / 2;
+}
+
+template <class P, bool FULL>
+__global__ void __launch_bounds__(CW_WARPS * 32) k_backpass_warp(Work w, Opts o, ParamBlock<P> pb, int iter)
+{
+    constexpr int NX = P::NX, NU = P::NU, NQXX = P::NQXX, NQUU = P::NQUU, NQXU = P::NQXU;
+    static_assert(sizeof(Dense<P>) == sizeof(double) * P::DENSE_SIZE, "Dense layout must match the generator's table");
+    __shared__ CoopWS<P> ws_all[CW_WARPS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int b = blockIdx.x * CW_WARPS + wid;
+    if (b >= w.B) return;
+    if (w.status[b] != ST_RUNNING) return;
+    CoopWS<P> &ws = ws_all[wid];
+    if (w.new_deriv[b]) {
+        if (w.deriv_fail[b]) {
+            if (lane == 0) finish(w, b, iter, w.bp_done[b] ? 1 : 0);
+            return;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            w.new_deriv[b] = 0;
+            w.n_dv[b] += 1;
+        }
+    }
+    const size_t Bp = w.Bp;
+    const int T = w.T;
+    const int cur = w.cur[b];
+    double lambda = w.lambda[b], dlambda = w.dlambda[b];
+    double *Dd = reinterpret_cast<double *>(&ws.D);
+    if (lane == 0) {
+        P::consts(pb.v, ws.D);
+        if (FULL) P::consts2(pb.v, ws.c2);
+    }
+    __syncwarp();
+
+    double dV0 = 0.0, dV1 = 0.0, g_sum = 0.0;
+    int n_bp = w.n_bp[b];
+    bool done = false;
+    while (!done) {
+        n_bp++;
+        for (int e = lane; e < NX; e += 32) ws.Vx[e] = w.FD[(size_t)e * Bp + b];
+        for (int e = lane; e < NQXX; e += 32) ws.Vxx[e] = w.FD[(size_t)(NX + e) * Bp + b];
+        dV0 = 0.0;
+        dV1 = 0.0;
+        g_sum = 0.0;
+        double lk[NU];
+#pragma unroll
+        for (int i = 0; i < NU; i++) lk[i] = 0.0;
+        bool failed = false;
+
+        for (int k = T - 1; k >= 0; k--) {
+            /* ---- load the time-varying entries of step k into the dense record ---- */
+            {
+                const double *rec = w.V1 + ((size_t)k * Bp + b) * P::NV1;
+                for (int j = lane; j < P::NV1; j += 32) Dd[P::v1_dst(j)] = rec[j];
+                if (FULL) {
+                    const double *rec2 = w.V2 + ((size_t)k * Bp + b) * P::NV2;
+                    for (int j = lane; j < P::NV2_USED; j += 32) ws.v2[j] = rec2[j];
+                }
+            }
+            __syncwarp();
+            /* ---- phase 1: Qu, Qx, Vxx*fu, Vxx*fx (back_pass.c:80-92, matMult.c first halves) ---- */
+            for (int e = lane; e < NU; e += 32) {
+                double acc = ws.D.cu[e];
+                for (int r = 0; r < NX; r++) acc += ws.Vx[r] * ws.D.fu[r + e * NX];
+                ws.Qu[e] = acc;
+            }
+            for (int e = lane; e < NX; e += 32) {
+                double acc = ws.D.cx[e];
+                for (int r = 0; r < NX; r++) acc += ws.Vx[r] * ws.D.fx[r + e * NX];
+                ws.Qx[e] = acc;
+            }
+            for (int e = lane; e < NX * NU; e += 32) {
+                const int r = e % NX, j = e / NX;
+                double acc = 0.0;
+                for (int s = 0; s < NX; s++) acc += ws.Vxx[symtri(r, s)] * ws.D.fu[s + j * NX];
+                ws.bc[e] = acc;
+            }
+            for (int e = lane; e < NX * NX; e += 32) {
+                const int r = e % NX, c = e / NX;
+                double acc = 0.0;
+                for (int s = 0; s < NX; s++) acc += ws.Vxx[symtri(r, s)] * ws.D.fx[s + c * NX];
+                ws.ba[e] = acc;
+            }
+            __syncwarp();
+            /* ---- phase 2: Qxu, Quu, Qxx (+ FULL_DDP terms; same lane owns the same entry in both) ---- */
+            for (int e = lane; e < NQXU; e += 32) {
+                const int i = e % NX, j = e / NX;
+                double acc = 0.0;
+                for (int s = 0; s < NX; s++) acc += ws.D.fx[s + i * NX] * ws.bc[s + j * NX];
+                double q = ws.D.cxu[e] + acc;
+                if (FULL) {
+                    const int t0 = P::s2xu_start(e), t1 = P::s2xu_start(e + 1);
+                    if (t1 > t0) {
+                        double d1 = 0.0;
+                        for (int t = t0; t < t1; t++) {
+                            const int src = P::s2xu_src(t);
+                            d1 += ws.Vx[P::s2xu_vx(t)] * (src >= 0 ? ws.v2[src] : ws.c2[-src - 1]);
+                        }
+                        q += d1;
+                    }
+                }
+                ws.Qxu[e] = q;
+            }
+            for (int e = lane; e < NQUU; e += 32) {
+                int r, c;
+                tri_rc(e, r, c);
+                double acc = 0.0;
+                for (int s = 0; s < NX; s++) acc += ws.D.fu[s + r * NX] * ws.bc[s + c * NX];
+                if (r != c) {
+                    for (int s = 0; s < NX; s++) acc += ws.D.fu[s + c * NX] * ws.bc[s + r * NX];
+                    acc *= 0.5;
+                }
+                double q = ws.D.cuu[e] + acc;
+                if (FULL) {
+                    const int t0 = P::s2uu_start(e), t1 = P::s2uu_start(e + 1);
+                    if (t1 > t0) {
+                        double d1 = 0.0;
+                        for (int t = t0; t < t1; t++) {
+                            const int src = P::s2uu_src(t);
+                            d1 += ws.Vx[P::s2uu_vx(t)] * (src >= 0 ? ws.v2[src] : ws.c2[-src - 1]);
+                        }
+                        q += d1;
+                    }
+                }
+                ws.Quu[e] = q;
+            }
+            for (int e = lane; e < NQXX; e += 32) {
+                int r, c;
+                tri_rc(e, r, c);
+                double acc = 0.0;
+                for (int s = 0; s < NX; s++) acc += ws.D.fx[s + r * NX] * ws.ba[s + c * NX];
+                if (r != c) {
+                    for (int s = 0; s < NX; s++) acc += ws.D.fx[s + c * NX] * ws.ba[s + r * NX];
+                    acc *= 0.5;
+                }
+                double q = ws.D.cxx[e] + acc;
+                if (FULL) {
+                    const int t0 = P::s2xx_start(e), t1 = P::s2xx_start(e + 1);
+                    if (t1 > t0) {
+                        double d1 = 0.0;
+                        for (int t = t0; t < t1; t++) {
+                            const int src = P::s2xx_src(t);
+                            d1 += ws.Vx[P::s2xx_vx(t)] * (src >= 0 ? ws.v2[src] : ws.c2[-src - 1]);
+                        }
+                        q += d1;
+                    }
+                }
+                ws.Qxx[e] = q;
+            }
+            __syncwarp();
+            /* ---- regularisation (back_pass.c:134-159) ---- */
+            for (int e = lane; e < NQUU; e += 32) ws.QuuF[e] = ws.Quu[e];
+            for (int e = lane; e < NQXU; e += 32) ws.Qxu_reg[e] = ws.Qxu[e];
+            __syncwarp();
+            if (o.regType == 2 && lane == 0) {
+                for (int j = 0; j < NU; j++)
+                    for (int i = 0; i <= j; i++) {
+                        double acc = 0.0;
+                        for (int c = 0; c < NU; c++) acc += ws.D.fu[symtri(c, i)] * ws.D.fu[symtri(c, j)];
+                        ws.QuuF[utri(i, j)] += acc * lambda;
+                    }
+                for (int i = 0; i < NX; i++)
+                    for (int j = 0; j < NU; j++) {
+                        double acc = 0.0;
+                        for (int c = 0; c < NX; c++) acc += ws.D.fx[c + i * NX] * ws.D.fu[(c + j * NU) < NX * NU ? (c + j * NU) : 0];
+                        ws.Qxu_reg[i + j * NX] += acc * lambda;
+                    }
+            }
+            if (o.regType == 1 && lane < NU) ws.QuuF[utri(lane, lane)] += lambda;
+            __syncwarp();
+            /* ---- box QP in every lane's registers (identical inputs -> identical results, uniform control flow) ---- */
+            int clamped[NU], n_free;
+            double invH[NQUU];
+            int qp;
+            {
+                double H[NQUU], g[NU], lo[NU], hi[NU];
+#pragma unroll
+                for (int i = 0; i < NQUU; i++) H[i] = ws.QuuF[i];
+#pragma unroll
+                for (int i = 0; i < NU; i++) {
+                    g[i] = ws.Qu[i];
+                    lo[i] = ws.D.lower[i];
+                    hi[i] = ws.D.upper[i];
+                }
+                qp = box_qp<NU>(H, g, lo, hi, lk, clamped, invH, n_free);
+            }
+            if (lane == 0) {
+                if (w.tr_clamp) {
+                    int code = (qp & 0xff) << 16;
+#pragma unroll
+                    for (int i = 0; i < NU; i++) code |= clamped[i] << (2 * i);
+                    w.tr_clamp[(size_t)k * Bp + b] = code;
+                }
+#pragma unroll
+                for (int i = 0; i < NU; i++) {
+                    ws.clamped[i] = clamped[i];
+                    ws.lk[i] = lk[i];
+                }
+#pragma unroll
+                for (int i = 0; i < NQUU; i++) ws.invH[i] = invH[i];
+            }
+            if (qp < 1) {
+                failed = true;
+                break;
+            }
+            __syncwarp();
+            /* ---- gains (back_pass.c:173-201), one entry per lane; also the control-law record of step k ---- */
+            {
+                double *rec = w.LL[cur] + ((size_t)k * Bp + b) * Rec<P>::RLL;
+                for (int e = lane; e < NU * NX; e += 32) {
+                    const int i = e % NU, s = e / NU;
+                    double acc = 0.0;
+                    if (ws.clamped[i]) {
+                        if (P::HAS_HX)
+                            acc -= (ws.clamped[i] == 1) ? ws.D.lower_sign[i] * ws.D.lower_hx[s + i * NX] : ws.D.upper_sign[i] * ws.D.upper_hx[s + i * NX];
+                    } else {
+                        for (int j = 0; j < NU; j++) {
+                            if (!ws.clamped[j]) {
+                                acc -= ws.invH[symtri(i, j)] * ws.Qxu_reg[s + j * NX];
+                            } else if (P::HAS_HX) {
+                                double wgt = 0.0;
+                                for (int c = 0; c < NU; c++)
+                                    if (!ws.clamped[c]) wgt -= ws.invH[symtri(i, c)] * ws.QuuF[symtri(c, j)];
+                                acc -= wgt * ((ws.clamped[j] == 1) ? ws.D.lower_sign[j] * ws.D.lower_hx[s + j * NX]
+                                                                    : ws.D.upper_sign[j] * ws.D.upper_hx[s + j * NX]);
+                            }
+                        }
+                    }
+                    ws.Lk[e] = acc;
+                    rec[NU + e] = acc;
+                }
+                for (int e = lane; e < NU; e += 32) rec[e] = lk[e];
+                for (int e = NU + NU * NX + lane; e < Rec<P>::RLL; e += 32) rec[e] = 0.0;
+            }
+            /* ---- expected reduction (back_pass.c:204-214), every lane keeps the same running sums ---- */
+#pragma unroll
+            for (int i = 0; i < NU; i++) dV0 += ws.Qu[i] * lk[i];
+#pragma unroll
+            for (int i = 0; i < NU; i++) {
+                double acc = 0.0;
+#pragma unroll
+                for (int j = 0; j < NU; j++) acc += lk[j] * ws.Quu[symtri(j, i)];
+                dV1 += 0.5 * lk[i] * acc;
+            }
+            __syncwarp();
+            /* ---- phase 3: Quu*l, Quu*L ---- */
+            for (int e = lane; e < NU; e += 32) {
+                double acc = 0.0;
+                for (int s = 0; s < NU; s++) acc += ws.Quu[symtri(e, s)] * ws.lk[s];
+                ws.bv[e] = acc;
+            }
+            for (int e = lane; e < NU * NX; e += 32) {
+                const int r = e % NU, c = e / NU;
+                double acc = 0.0;
+                for (int s = 0; s < NU; s++) acc += ws.Quu[symtri(r, s)] * ws.Lk[s + c * NU];
+                ws.bl[e] = acc;
+            }
+            __syncwarp();
+            /* ---- phase 4: value function (back_pass.c:217-241) ---- */
+            for (int e = lane; e < NX; e += 32) {
+                double acc = 0.0;
+                for (int s = 0; s < NU; s++) acc += ws.Lk[s + e * NU] * ws.bv[s];
+                double v = ws.Qx[e] + acc;
+                for (int j = 0; j < NU; j++) v += ws.Lk[j + e * NU] * ws.Qu[j];
+                for (int j = 0; j < NU; j++) v += ws.Qxu[e + j * NX] * ws.lk[j];
+                ws.Vx[e] = v;
+            }
+            for (int e = lane; e < NQXX; e += 32) {
+                int r, c;
+                tri_rc(e, r, c);
+                double acc = 0.0;
+                for (int s = 0; s < NU; s++) acc += ws.Lk[s + r * NU] * ws.bl[s + c * NU];
+                if (r != c) {
+                    for (int s = 0; s < NU; s++) acc += ws.Lk[s + c * NU] * ws.bl[s + r * NU];
+                    acc *= 0.5;
+                }
+                double v = ws.Qxx[e] + acc;
+                if (r == c) {
+                    for (int cc = 0; cc < NU; cc++) {
+                        double term = ws.Lk[cc + r * NU] * ws.Qxu[r + cc * NX];
+                        term *= 2.0;
+                        v += term;
+                    }
+                } else { /* the reference's loop visits (i=r, j=c) before (i=c, j=r) for r < c */
+                    for (int cc = 0; cc < NU; cc++) v += ws.Lk[cc + r * NU] * ws.Qxu[c + cc * NX];
+                    for (int cc = 0; cc < NU; cc++) v += ws.Lk[cc + c * NU] * ws.Qxu[r + cc * NX];
+                }
+                ws.Vxx[e] = v;
+            }
+            /* ---- gradient measure (back_pass.c:244-251) ---- */
+            {
+                const double *un = w.XU[cur] + ((size_t)k * Bp + b) * Rec<P>::RXU + NX;
+                double gmax = 0.0;
+#pragma unroll
+                for (int i = 0; i < NU; i++) {
+                    const double gi = fabs(lk[i]) / (fabs(un[i]) + 1.0);
+                    if (gi > gmax) gmax = gi;
+                }
+                g_sum += gmax;
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+        if (failed) {
+            raise_lambda(o, lambda, dlambda);
+            if (lambda > o.lambdaMax) break;
+        } else {
+            done = true;
+        }
+    }
+    if (lane != 0) return;
+    w.n_bp[b] = n_bp;
+    w.dV0[b] = dV0;
+    w.dV1[b] = dV1;
+    w.bp_done[b] = done ? 1 : 0;
+    double g_norm = w.g_norm[b];
+    if (done) {
+        g_norm = g_sum / ((double)(T - 1));
+        w.g_norm[b] = g_norm;
+    }
+    if (g_norm < o.tolGrad && lambda < 1e-5) {
         lower_lambda(o, lambda, dlambda);
         finish(w, b, iter, done ? 1 : 0);
     } else if (!done) {

@@ -141,6 +141,7 @@ def emit_device(m, struct_name) -> str:
     o.append(f"    static constexpr int NV1 = {nv1}, NV2 = {max(nv2, 1)}, NV2_USED = {nv2};")
     o.append(f"    static constexpr int OFF_LOWER = {off_lower}, OFF_UPPER = {off_upper};")
     o.append(f"    static constexpr int NH = {len(m.h)};")
+    o.append(f"    static constexpr bool COOP = {'true' if nx > 6 else 'false'};   /* warp-cooperative backward pass (state too large for one lane) */")
     o.append(f"    static const char *name() {{ return \"{m.name}\"; }}")
     o.append("    static int param_count() { return %d; }" % len(m.params))
     o.append("    static const char *param_name(int i) { const char *n[] = {%s}; return n[i]; }"
@@ -331,6 +332,56 @@ def emit_device(m, struct_name) -> str:
     pre, body = contraction(m.fuu, v2_pos, m.nquu, "Quu"); o.append(pre); o.append(body); o.append("    }")
     o.append("    __device__ __forceinline__ static void add2_Qxx(const double *Vx, const double *v2, const double *p, double *Qxx) {\n        (void)Vx; (void)v2; (void)p; (void)Qxx;")
     pre, body = contraction(m.fxx, v2_pos, m.nqxx, "Qxx"); o.append(pre); o.append(body); o.append("    }\n")
+
+    # ---- data-driven forms for the warp-cooperative backward pass ------------------------------------------------------
+    # (a) destination of every stored time-varying entry inside the dense per-step record (struct Dense in
+    #     ilqg_kernels.cuh: fx fu cx cxx cu cuu cxu lower upper lower_sign upper_sign lower_hx upper_hx, contiguous doubles)
+    offs, acc_ = {}, 0
+    for key, size in (("fx", nx * nx), ("fu", nx * nu), ("cx", nx), ("cxx", m.nqxx), ("cu", nu), ("cuu", m.nquu), ("cxu", m.nqxu),
+                      ("lower", nu), ("upper", nu), ("lower_sign", nu), ("upper_sign", nu), ("lower_hx", nx * nu), ("upper_hx", nx * nu)):
+        offs[key] = acc_
+        acc_ += size
+    dst = [offs[k] + e.idx for k, e in v1] + [offs["lower"] + i for i in range(nu)] + [offs["upper"] + i for i in range(nu)]
+    if m.has_hx:
+        dst += [offs["lower_sign"] + i for i in range(nu)] + [offs["upper_sign"] + i for i in range(nu)]
+        dst += [offs["lower_hx"] + i for i in range(nx * nu)] + [offs["upper_hx"] + i for i in range(nx * nu)]
+    assert len(dst) == nv1
+    o.append("    static constexpr int DENSE_SIZE = %d;" % acc_)
+    o.append("    __device__ __forceinline__ static int v1_dst(int j) { static constexpr unsigned short t[] = {%s}; return t[j]; }"
+             % ", ".join(str(d) for d in dst))
+    # (b) FULL_DDP contractions as sparse term lists per output entry (reference loop: back_pass.c:95-131); constant
+    #     (parameter-only) tensor entries get slots in c2[], filled once by consts2()
+    sck2 = Scope("q")
+    c2_slots = []
+
+    def csr(entries, pos, nout, key):
+        ent = {e.idx: e for e in entries}
+        start, vi, src = [0], [], []
+        for j in range(nout):
+            for i in range(nx):
+                e = ent[j + i * nout]
+                if e.expr == 0:
+                    continue
+                vi.append(i)
+                if e.time_var:
+                    src.append(pos[(key, e.idx)])
+                else:
+                    c2_slots.append(e.expr)
+                    src.append(-len(c2_slots))
+            start.append(len(vi))
+        return start, vi, src
+
+    for nm, entries, nout, key in (("xu", m.fxu, m.nqxu, "fxu"), ("uu", m.fuu, m.nquu, "fuu"), ("xx", m.fxx, m.nqxx, "fxx")):
+        start, vi, src = csr(entries, v2_pos, nout, key)
+        o.append("    __device__ __forceinline__ static int s2%s_start(int j) { static constexpr unsigned short t[] = {%s}; return t[j]; }" % (nm, ", ".join(map(str, start))))
+        o.append("    __device__ __forceinline__ static int s2%s_vx(int t_) { static constexpr unsigned char t[] = {%s}; return t[t_]; }" % (nm, ", ".join(map(str, vi + [0]))))
+        o.append("    __device__ __forceinline__ static int s2%s_src(int t_) { static constexpr short t[] = {%s}; return t[t_]; }" % (nm, ", ".join(map(str, src + [0]))))
+    o.append("    static constexpr int NC2 = %d;" % max(len(c2_slots), 1))
+    for i, e in enumerate(c2_slots):
+        sck2.out(("arr", "c2", i), e, False)
+    o.append("    __device__ __forceinline__ static void consts2(const double *p, double *c2) {\n        (void)p; (void)c2;")
+    o.append(render(sck2, NR, aux_t, guards=False))
+    o.append("    }\n")
 
     # ---- multiplier updates ----------------------------------------------------------------------------------------------
     # h values of the constraints of one context, evaluated from the state (the reference reads the aux value the

@@ -1,3 +1,3 @@
-from . import car, brachi  # noqa: F401
+from . import brachi, car, quad  # noqa: F401
 
-REGISTRY = {"car": car.define, "brachi": brachi.define}
+REGISTRY = {"car": car.define, "brachi": brachi.define, "quad": quad.define}

@@ -73,3 +73,22 @@ def brachi(n):
     u0 = -np.ones((n, 1))
     opts = {"max_iter": 20.0, "w_pen_fact2": 2.0}
     return params, x0, u0, opts
+
+
+# ---- synthetic quadrotor (config 5) ---------------------------------------------------------------------------------
+QUAD_T = 1000
+_QUAD_UH = 1.0 * 9.81 / 4.0
+QUAD_PARAMS = {
+    "dt": [0.01], "mass": [1.0], "grav": [9.81], "J": [0.01, 0.01, 0.02], "arm": [0.2], "kq": [0.05],
+    "cx": [1e-3] * 3 + [1e-4] * 3 + [1e-3] * 3 + [1e-4] * 3,
+    "cf": [10.0] * 3 + [1.0] * 3 + [10.0] * 3 + [1.0] * 3,
+    "cu": [1e-3] * 4, "xg": [0.0] * 12, "uh": [_QUAD_UH], "ulim": [0.0, 2.0 * _QUAD_UH],
+}
+
+
+def quad_batch(B, T=QUAD_T, seed=3, first=0):
+    """x0 = hover at the origin + U(-0.5, 0.5) on every state, u0 = hover thrust on all rotors."""
+    b = np.arange(first, first + B, dtype=np.uint64)
+    x0 = np.stack([-0.5 + uniform01(seed, b, i) for i in range(12)], axis=1)
+    u0 = np.full((B, T, 4), _QUAD_UH)
+    return x0, u0

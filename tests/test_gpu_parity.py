@@ -57,3 +57,18 @@ def test_car_batch_matches_oracle():
     for b in range(B):
         ora = PU.oracle_record(kind, "car", 0, 500, W.CAR_PARAMS, x0[b], u0[b], opts)
         PU.assert_same(recs[b], ora, f"car batch b{b} vs {kind}")
+
+
+@pytest.mark.parametrize("ddp", [1, 0])
+def test_quadrotor_matches_oracle(ddp):
+    """BASELINE config 5 parity subset: synthetic quadrotor n=12, m=4, T=1000 (warp-cooperative backward pass; FULL_DDP=1
+    exercises the regularisation retry loop: ~44 back passes for 24 passes)."""
+    B, T = 4, 1000
+    x0, u0 = W.quad_batch(B, T=T)
+    opts = {"max_iter": 30 if ddp else 12}
+    recs = PU.gpu_records("quad", ddp, T, W.QUAD_PARAMS, x0, u0, opts)
+    kind = PU.oracle_kinds("quad", ddp)[0]
+    for b in range(B):
+        ora = PU.oracle_record(kind, "quad", ddp, T, W.QUAD_PARAMS, x0[b], u0[b], opts)
+        PU.assert_same(recs[b], ora, f"quad ddp{ddp} b{b} vs {kind}", keys=("result", "iterations", "n_ls", "n_bp", "cost", "lambda", "g_norm",
+                                                                            "tr_alpha", "tr_lambda", "tr_newcost", "x", "u", "l", "L", "dV0", "dV1"))
