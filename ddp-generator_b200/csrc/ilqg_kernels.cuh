@@ -715,6 +715,9 @@ __global__ void __launch_bounds__(BP_BLOCK, ILQG_BP_MINBLOCKS) k_backpass(Work w
  * sparse term lists emitted by the generator.
  * ===================================================================================================================== */
 constexpr int CW_WARPS = 4;
+#ifndef ILQG_CW_MINBLOCKS
+#define ILQG_CW_MINBLOCKS 4   /* 128 registers: 16 warps per SM; measured best of 1/3/4/5 on the quadrotor */
+#endif
 
 template <class P> struct CoopWS {
     Dense<P> D;
@@ -733,7 +736,7 @@ __device__ __forceinline__ void tri_rc(int e, int &r, int &c)
 }
 
 template <class P, bool FULL>
-__global__ void __launch_bounds__(CW_WARPS * 32) k_backpass_warp(Work w, Opts o, ParamBlock<P> pb, int iter)
+__global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_warp(Work w, Opts o, ParamBlock<P> pb, int iter)
 {
     constexpr int NX = P::NX, NU = P::NU, NQXX = P::NQXX, NQUU = P::NQUU, NQXU = P::NQXU;
     static_assert(sizeof(Dense<P>) == sizeof(double) * P::DENSE_SIZE, "Dense layout must match the generator's table");

@@ -118,6 +118,11 @@ def main():
         for ddp in (0, 1):
             np.savez_compressed(os.path.join(HERE, f"brachi_n{n}_ddp{ddp}.npz"),
                                 **solve_fixture("brachi", ddp, n, params, bx0, bu0, opts))
+    xq, uq = W.quad_batch(2, T=300)
+    for b in range(2):
+        for ddp in (0, 1):
+            np.savez_compressed(os.path.join(HERE, f"quad_T300_b{b}_ddp{ddp}.npz"),
+                                **solve_fixture("quad", ddp, 300, W.QUAD_PARAMS, xq[b], uq[b], {"max_iter": 25}))
     np.savez_compressed(os.path.join(HERE, "kats.npz"), **kats())
     # bit patterns of the deterministic math layer on a fixed grid
     lib = C.CDLL(os.path.join(ROOT, "oracle", "_build", "libdmcheck.so"))

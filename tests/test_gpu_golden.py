@@ -35,6 +35,14 @@ def test_car_single_golden(ddp):
         assert np.array_equal(((code >> 16) & 0xff)[::-1], g["qp_ret_last"])
 
 
+@pytest.mark.parametrize("ddp", [0, 1])
+def test_quad_golden(ddp):
+    gs = [np.load(os.path.join(GOLD, f"quad_T300_b{b}_ddp{ddp}.npz")) for b in range(2)]
+    recs = PU.gpu_records("quad", ddp, 300, W.QUAD_PARAMS, np.stack([g["x0"] for g in gs]), np.stack([g["u0"] for g in gs]), {"max_iter": 25})
+    for b, g in enumerate(gs):
+        PU.assert_same(recs[b], {k: g[k] for k in KEYS}, f"quad_T300_b{b}_ddp{ddp}", keys=KEYS)
+
+
 @pytest.mark.parametrize("n", [2, 3, 5, 500])
 @pytest.mark.parametrize("ddp", [0, 1])
 def test_brachi_golden(n, ddp):

@@ -55,6 +55,12 @@ def test_brachistochrone(n, ddp):
     check_solve(f"brachi_n{n}_ddp{ddp}.npz", "brachi", ddp, n, params, opts)
 
 
+@pytest.mark.parametrize("b", [0, 1])
+@pytest.mark.parametrize("ddp", [0, 1])
+def test_quadrotor(b, ddp):
+    check_solve(f"quad_T300_b{b}_ddp{ddp}.npz", "quad", ddp, 300, W.QUAD_PARAMS, {"max_iter": 25})
+
+
 def test_brachistochrone_reaches_cycloid_time():
     """Sanity of the fixture itself: n=500 converges towards the analytic cycloid time pi*sqrt(2/g)."""
     g = np.load(os.path.join(GOLD, "brachi_n500_ddp0.npz"))
