@@ -93,8 +93,15 @@ int ilqgk_launch_backpass(const ilqg_work *w, const ilqg_opts *o, const double *
 {
     if constexpr (use_coop<P>())
         k_backpass_warp<P, FULL_DDP != 0><<<nblk(w->B, CW_WARPS), CW_WARPS * 32, 0, (cudaStream_t)stream>>>(*w, *o, make_pb(params), iter);
-    else
-        k_backpass<P, FULL_DDP != 0><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, make_pb(params), iter);
+    else {
+        constexpr size_t smem = sizeof(double) * 2 * bp_fields<P, FULL_DDP != 0>() * BP_BLOCK;
+        static bool configured = false;
+        if (!configured) {
+            if (check(cudaFuncSetAttribute(k_backpass<P, FULL_DDP != 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return -1;
+            configured = true;
+        }
+        k_backpass<P, FULL_DDP != 0><<<nblk(w->B, BP_BLOCK), BP_BLOCK, smem, (cudaStream_t)stream>>>(*w, *o, make_pb(params), iter);
+    }
     return check(cudaGetLastError(), "k_backpass");
 }
 

@@ -176,7 +176,7 @@ static int push_params(ilqgb_handle *h, tOptSet *o)
 {
     int i;
     for (i = 0; i < n_params; i++)
-        if (ilqgb_set_param(h, i, o->p[i], paramdesc[i]->size)) return -1;
+        if (ilqgb_set_param(h, i, o->p[i], paramdesc[i]->size == -1 ? o->n_hor + 1 : paramdesc[i]->size)) return -1;
     return 0;
 }
 

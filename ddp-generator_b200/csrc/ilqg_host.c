@@ -29,6 +29,8 @@ struct chunk {
     ilqg_work w;
     ilqg_opts o;
     double *params;        /* flat, time-invariant */
+    double *d_kp[16];      /* [k]-indexed parameters: device arrays of n_hor + 1 doubles, in parameter order */
+    double **d_pk;         /* device table of those pointers (ilqg_work.pk) */
     void *stream;
     int owns_stream;
     int iter;              /* pass index of the running problems */
@@ -205,7 +207,15 @@ static int ck_set_param(chunk *h, int index, const double *value, int n)
 {
     int i, off = 0;
     if (index < 0 || index >= ilqgk_param_count()) return fail(h, "parameter index out of range");
-    if (ilqgk_param_size(index) == -1) return fail(h, "[k]-indexed parameters are not supported by this build");
+    if (ilqgk_param_size(index) == -1) { /* one value per timestep, name[k] in the problem file */
+        int kidx = 0;
+        if (n != h->T + 1) return fail(h, "wrong parameter length (n_hor + 1 expected)");
+        for (i = 0; i < index; i++)
+            if (ilqgk_param_size(i) == -1) kidx++;
+        if (ilqgk_set_device(h->device)) return failk(h);
+        if (ilqgk_h2d(h->d_kp[kidx], value, sizeof(double) * n, h->stream) || ilqgk_stream_sync(h->stream)) return failk(h);
+        return 0;
+    }
     if (n != ilqgk_param_size(index)) return fail(h, "wrong parameter length");
     for (i = 0; i < index; i++)
         if (ilqgk_param_size(i) > 0) off += ilqgk_param_size(i);
@@ -243,8 +253,8 @@ static chunk *ck_create(int device, int batch, int n_hor, int flags, void *strea
     h->T = n_hor;
     h->flags = flags;
     ilqgk_dims(&h->d);
-    if (h->d.nkp > 0) {
-        fail(NULL, "[k]-indexed parameters are not supported by this build");
+    if (h->d.nkp > 16) {
+        fail(NULL, "too many [k]-indexed parameters");
         free(h);
         return NULL;
     }
@@ -278,6 +288,15 @@ static chunk *ck_create(int device, int batch, int n_hor, int flags, void *strea
         DALLOC(w->muF, double, d->n_mu_f * Bp + 1);
         DALLOC(w->lastF, double, d->n_mu_f * Bp + 1);
         w->pk = NULL;
+        if (d->nkp > 0) {
+            for (i = 0; i < d->nkp; i++) {
+                DALLOC(h->d_kp[i], double, T + 1);
+                ilqgk_memset(h->d_kp[i], 0, sizeof(double) * (T + 1), h->stream);
+            }
+            DALLOC(h->d_pk, double *, d->nkp);
+            if (ilqgk_h2d(h->d_pk, h->d_kp, sizeof(double *) * d->nkp, h->stream) || ilqgk_stream_sync(h->stream)) goto oom;
+            w->pk = (const double *const *)h->d_pk;
+        }
         DALLOC(w->cost, double, Bp);
         DALLOC(w->new_cost, double, Bp);
         DALLOC(w->dcost, double, Bp);

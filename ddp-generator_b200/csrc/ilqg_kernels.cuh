@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(BP_BLOCK, ILQG_BP_MINBLOCKS) k_backpass(Work w
 {
     constexpr int NX = P::NX, NU = P::NU, NQXX = P::NQXX, NQUU = P::NQUU, NQXU = P::NQXU;
     constexpr int NF = bp_fields<P, FULL>();
-    __shared__ double sm[2 * NF * BP_BLOCK];
+    extern __shared__ double sm[];   /* 2 stages x NF fields x BP_BLOCK columns (dynamic: can exceed 48 KB) */
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= w.B) return;
     if (w.status[b] != ST_RUNNING) return;

@@ -92,3 +92,16 @@ def quad_batch(B, T=QUAD_T, seed=3, first=0):
     x0 = np.stack([-0.5 + uniform01(seed, b, i) for i in range(12)], axis=1)
     u0 = np.full((B, T, 4), _QUAD_UH)
     return x0, u0
+
+
+# ---- car with a state-dependent steering limit (reference extension: state dependent input constraints) -------------
+CARHX_PARAMS = dict(CAR_PARAMS, kv=[0.5])
+
+
+# ---- Brachistochrone with a running inequality and a [k]-indexed parameter (testBrachi_hli.m:7-32) -----------------
+def brachi_hli(n=500):
+    params = {"dx": [2.0 * np.pi / n], "g": [9.81], "ymin": np.concatenate([np.linspace(-1.0, -5.0, n), [-4.0]])}
+    x0 = np.array([-np.finfo(float).eps])
+    u0 = -np.ones((n, 1))
+    opts = {"max_iter": 20.0, "w_pen_init_l": 40.0, "w_pen_init_f": 1e-5, "w_pen_max_f": 1.0, "w_pen_fact2": 1.0}
+    return params, x0, u0, opts

@@ -123,6 +123,17 @@ def main():
         for ddp in (0, 1):
             np.savez_compressed(os.path.join(HERE, f"quad_T300_b{b}_ddp{ddp}.npz"),
                                 **solve_fixture("quad", ddp, 300, W.QUAD_PARAMS, xq[b], uq[b], {"max_iter": 25}))
+    xs, us = W.car_single()
+    for ddp in (0, 1):
+        np.savez_compressed(os.path.join(HERE, f"carhx_ddp{ddp}.npz"),
+                            **solve_fixture("carhx", ddp, 500, W.CARHX_PARAMS, xs, us, {"max_iter": 60}, with_qp=True))
+    params, bx0, bu0, opts = W.brachi_hli(500)
+    for ddp in (0, 1):
+        fx = solve_fixture("brachi_hli", ddp, 500, params, bx0, bu0, opts)
+        s = oracle_lib.OracleLib("reference", "brachi_hli", ddp).solver(500)
+        s.set_opts(opts); s.set_params(params); s.init(bx0, bu0); s.solve()
+        fx["mult_t"] = s.get("mult_t")
+        np.savez_compressed(os.path.join(HERE, f"brachi_hli_ddp{ddp}.npz"), **fx)
     np.savez_compressed(os.path.join(HERE, "kats.npz"), **kats())
     # bit patterns of the deterministic math layer on a fixed grid
     lib = C.CDLL(os.path.join(ROOT, "oracle", "_build", "libdmcheck.so"))

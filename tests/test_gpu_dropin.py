@@ -51,6 +51,16 @@ def test_brachi_through_reference_api(n):
     compare("brachi", 0, n, params, x0, u0, opts)
 
 
+def test_brachi_hli_through_reference_api():
+    params, x0, u0, opts = W.brachi_hli(500)
+    compare("brachi_hli", 0, 500, params, x0, u0, opts)
+
+
+def test_carhx_through_reference_api():
+    x0, u0 = W.car_single()
+    compare("carhx", 0, 500, W.CARHX_PARAMS, x0, u0, {"max_iter": 40})
+
+
 def test_option_errors_through_reference_api():
     s = oracle_lib.OracleLib("b200", "car", 0).solver(4)
     assert s.set_opt_raw("zMin", 1.0) == "parameter must be in range [0..1)"

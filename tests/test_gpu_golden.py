@@ -36,6 +36,32 @@ def test_car_single_golden(ddp):
 
 
 @pytest.mark.parametrize("ddp", [0, 1])
+def test_car_state_dependent_limits_golden(ddp):
+    """State-dependent input constraints (hx != 0): the active constraint's gradient enters the gains of clamped inputs."""
+    g = np.load(os.path.join(GOLD, f"carhx_ddp{ddp}.npz"))
+    rec = PU.gpu_records("carhx", ddp, 500, W.CARHX_PARAMS, g["x0"], g["u0"], {"max_iter": 60})[0]
+    PU.assert_same(rec, {k: g[k] for k in KEYS}, f"carhx_ddp{ddp}", keys=KEYS)
+    if (g["qp_ret_last"] >= 1).all():
+        code = rec["tr_clamp"]
+        assert np.array_equal(np.stack([code & 3, (code >> 2) & 3], axis=1)[::-1], g["qp_clamped_last"])
+
+
+@pytest.mark.parametrize("ddp", [0, 1])
+def test_brachi_running_inequality_golden(ddp):
+    """hli running inequality (Ruxton multiplier update), terminal equality and a [k]-indexed parameter."""
+    import ilqg_b200
+    g = np.load(os.path.join(GOLD, f"brachi_hli_ddp{ddp}.npz"))
+    params, _, _, opts = W.brachi_hli(500)
+    rec = PU.gpu_records("brachi_hli", ddp, 500, params, g["x0"][None], g["u0"][None], opts)[0]
+    PU.assert_same(rec, {k: g[k] for k in KEYS}, f"brachi_hli_ddp{ddp}", keys=KEYS)
+    s = ilqg_b200.BatchSolver("brachi_hli", ddp, 1, 500)
+    s.set_options(opts); s.set_params(params); s.solve(g["x0"][None], g["u0"][None])
+    assert s.get("mu_f").ravel()[0] == g["mult_f"][0]
+    assert np.array_equal(s.get("mu_r").reshape(500), g["mult_t"][:, 0])      # running multipliers mu_li[k]
+    s.close()
+
+
+@pytest.mark.parametrize("ddp", [0, 1])
 def test_quad_golden(ddp):
     gs = [np.load(os.path.join(GOLD, f"quad_T300_b{b}_ddp{ddp}.npz")) for b in range(2)]
     recs = PU.gpu_records("quad", ddp, 300, W.QUAD_PARAMS, np.stack([g["x0"] for g in gs]), np.stack([g["u0"] for g in gs]), {"max_iter": 25})

@@ -61,6 +61,19 @@ def test_quadrotor(b, ddp):
     check_solve(f"quad_T300_b{b}_ddp{ddp}.npz", "quad", ddp, 300, W.QUAD_PARAMS, {"max_iter": 25})
 
 
+@pytest.mark.parametrize("ddp", [0, 1])
+def test_car_state_dependent_limits(ddp):
+    check_solve(f"carhx_ddp{ddp}.npz", "carhx", ddp, 500, W.CARHX_PARAMS, {"max_iter": 60}, with_qp=True)
+
+
+@pytest.mark.parametrize("ddp", [0, 1])
+def test_brachistochrone_running_inequality(ddp):
+    params, _, _, opts = W.brachi_hli(500)
+    check_solve(f"brachi_hli_ddp{ddp}.npz", "brachi_hli", ddp, 500, params, opts)
+    g = np.load(os.path.join(GOLD, f"brachi_hli_ddp{ddp}.npz"))
+    assert (g["x"][:, 0] - params["ymin"]).min() > -1e-5      # the path respects the running bound y >= ymin[k]
+
+
 def test_brachistochrone_reaches_cycloid_time():
     """Sanity of the fixture itself: n=500 converges towards the analytic cycloid time pi*sqrt(2/g)."""
     g = np.load(os.path.join(GOLD, "brachi_n500_ddp0.npz"))
