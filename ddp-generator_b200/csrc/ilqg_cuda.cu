@@ -118,6 +118,16 @@ int ilqgk_launch_ls_round(const ilqg_work *w, const ilqg_opts *o, const double *
     return check(cudaGetLastError(), "k_ls_round");
 }
 
+int ilqgk_launch_ls_tail(const ilqg_work *w, const ilqg_opts *o, const double *params, int iter, int from, void *stream)
+{
+    const int nrem = o->n_alpha - from;
+    const ParamBlock<P> pb = make_pb(params);
+    k_ls_tail<P><<<nblk(w->B * nrem, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, pb, from);
+    if (check(cudaGetLastError(), "k_ls_tail")) return -1;
+    k_ls_commit<P><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, pb, iter, from);
+    return check(cudaGetLastError(), "k_ls_commit");
+}
+
 int ilqgk_launch_post(const ilqg_work *w, const ilqg_opts *o, const double *params, void *stream)
 {
     if (P::N_MU_R + P::N_MU_F == 0) return 0;   /* cost does not depend on multipliers/penalties: nothing to redo */

@@ -45,6 +45,7 @@ int ilqgk_launch_derivs(const ilqg_work *w, const double *params, void *stream);
 int ilqgk_launch_backpass(const ilqg_work *w, const ilqg_opts *o, const double *params, int iter, void *stream);
 int ilqgk_launch_ls_reset(const ilqg_work *w, void *stream);
 int ilqgk_launch_ls_round(const ilqg_work *w, const ilqg_opts *o, const double *params, int iter, int round, void *stream);
+int ilqgk_launch_ls_tail(const ilqg_work *w, const ilqg_opts *o, const double *params, int iter, int from, void *stream);
 int ilqgk_launch_post(const ilqg_work *w, const ilqg_opts *o, const double *params, void *stream);
 int ilqgk_has_post(void);
 int ilqgk_launch_finalize(const ilqg_work *w, int max_iter, void *stream);

@@ -34,6 +34,7 @@ struct chunk {
     void *stream;
     int owns_stream;
     int iter;              /* pass index of the running problems */
+    int ls_tail_from;      /* -1 = choose by batch size */
     int started;
     int trace_cap;         /* max_iter the trace arrays were sized for */
     void **allocs;
@@ -252,6 +253,7 @@ static chunk *ck_create(int device, int batch, int n_hor, int flags, void *strea
     h->Bp = (batch + 31) / 32 * 32;
     h->T = n_hor;
     h->flags = flags;
+    h->ls_tail_from = getenv("ILQG_LS_TAIL_FROM") ? atoi(getenv("ILQG_LS_TAIL_FROM")) : -1;
     ilqgk_dims(&h->d);
     if (h->d.nkp > 16) {
         fail(NULL, "too many [k]-indexed parameters");
@@ -321,6 +323,8 @@ static chunk *ck_create(int device, int batch, int n_hor, int flags, void *strea
         DALLOC(w->ls_list[0], int, Bp);
         DALLOC(w->ls_list[1], int, Bp);
         DALLOC(w->ls_count, int, ILQG_MAX_ALPHA + 2);
+        DALLOC(w->ls_cnew, double, (size_t)ILQG_MAX_ALPHA * Bp);
+        DALLOC(w->ls_mask, int, Bp);
         DALLOC(w->n_dv, int, Bp);
         DALLOC(w->n_roll, int, Bp);
         ilqgk_memset(w->status, 0, sizeof(int) * Bp, h->stream);
@@ -525,11 +529,24 @@ static int launch_pass(chunk *h, int do_derivs, int do_back, int do_ls)
     if (do_ls) {
         int r;
         if (ilqgk_launch_ls_reset(&h->w, h->stream)) return failk(h);
-        for (r = 0; r < h->o.n_alpha; r++) {
-            p = timing_begin(h, TC_LINESEARCH);
-            if (ilqgk_launch_ls_round(&h->w, &h->o, h->params, h->iter, r, h->stream)) return failk(h);
-            h->n_launches++;
-            timing_end(h, p);
+        {
+            /* small batches: one sequential round, then all remaining alphas at once (latency-bound regime);
+               large batches: one alpha per launch over the shrinking list of undecided problems (throughput-bound) */
+            int from = h->ls_tail_from >= 0 ? h->ls_tail_from : (h->B <= 40000 ? 1 : (h->B <= 100000 ? 3 : h->o.n_alpha));
+            if (from > h->o.n_alpha || h->o.n_alpha - from < 2) from = h->o.n_alpha;
+            h->o.ls_tail_from = from;
+            for (r = 0; r < from; r++) {
+                p = timing_begin(h, TC_LINESEARCH);
+                if (ilqgk_launch_ls_round(&h->w, &h->o, h->params, h->iter, r, h->stream)) return failk(h);
+                h->n_launches++;
+                timing_end(h, p);
+            }
+            if (from < h->o.n_alpha) {
+                p = timing_begin(h, TC_LINESEARCH);
+                if (ilqgk_launch_ls_tail(&h->w, &h->o, h->params, h->iter, from, h->stream)) return failk(h);
+                h->n_launches += 2;
+                timing_end(h, p);
+            }
         }
         if (ilqgk_has_post()) {
             p = timing_begin(h, TC_POST);

@@ -58,18 +58,27 @@ __device__ __forceinline__ double dmin(double a, double b) { return (a < b) ? a 
 __host__ __device__ constexpr int utri(int r, int c) { return (c * (c + 1)) / 2 + r; }
 __host__ __device__ constexpr int symtri(int r, int c) { return r > c ? utri(c, r) : utri(r, c); }
 
-/* ---- small dense algebra, operation order of matMult.c ---------------------------------------------------------- */
-template <int NR, int NC>
+/* ---- small dense algebra, operation order of matMult.c ----------------------------------------------------------
+ * MA / MC are compile-time masks of the structurally non-zero entries of the operands a / c (generated per problem;
+ * AllNZ for run-time dense operands).  A term whose factor is structurally zero is skipped: it could only add +-0 to
+ * a finite sum, so every non-zero result is unchanged.  -DILQG_EXPLOIT_ZEROS=0 keeps all terms. */
+#ifndef ILQG_EXPLOIT_ZEROS
+#define ILQG_EXPLOIT_ZEROS 1
+#endif
+struct AllNZ { __host__ __device__ static constexpr bool nz(int) { return true; } };
+template <class M> __host__ __device__ constexpr bool mnz(int i) { return !ILQG_EXPLOIT_ZEROS || M::nz(i); }
+
+template <int NR, int NC, class MB = AllNZ>
 __device__ __forceinline__ void add_mul_vec(double *base, const double *a, const double *b)
 {
 #pragma unroll
     for (int c = 0; c < NC; c++)
 #pragma unroll
         for (int r = 0; r < NR; r++)
-            base[c] += a[r] * b[r + c * NR];
+            if (mnz<MB>(r + c * NR)) base[c] += a[r] * b[r + c * NR];
 }
 
-template <int NR, int NC>
+template <int NR, int NC, class MA = AllNZ>
 __device__ __forceinline__ void add_square_tri(double *base, const double *B, const double *a)
 {
     double ba[NR * NC];
@@ -80,7 +89,7 @@ __device__ __forceinline__ void add_square_tri(double *base, const double *B, co
             double acc = 0.0;
 #pragma unroll
             for (int s = 0; s < NR; s++)
-                acc += B[symtri(r, s)] * a[s + c * NR];
+                if (mnz<MA>(s + c * NR)) acc += B[symtri(r, s)] * a[s + c * NR];
             ba[r + c * NR] = acc;
         }
 #pragma unroll
@@ -90,18 +99,18 @@ __device__ __forceinline__ void add_square_tri(double *base, const double *B, co
             double acc = 0.0;
 #pragma unroll
             for (int s = 0; s < NR; s++)
-                acc += a[s + r * NR] * ba[s + c * NR];
+                if (mnz<MA>(s + r * NR)) acc += a[s + r * NR] * ba[s + c * NR];
             if (r != c) {
 #pragma unroll
                 for (int s = 0; s < NR; s++)
-                    acc += a[s + c * NR] * ba[s + r * NR];
+                    if (mnz<MA>(s + c * NR)) acc += a[s + c * NR] * ba[s + r * NR];
                 acc *= 0.5;
             }
             base[utri(r, c)] += acc;
         }
 }
 
-template <int NRA, int NCA, int NCC>
+template <int NRA, int NCA, int NCC, class MA = AllNZ, class MC = AllNZ>
 __device__ __forceinline__ void add_mul2_tri(double *base, const double *B, const double *a, const double *c)
 {
     double bc[NRA * NCC];
@@ -112,7 +121,7 @@ __device__ __forceinline__ void add_mul2_tri(double *base, const double *B, cons
             double acc = 0.0;
 #pragma unroll
             for (int s = 0; s < NRA; s++)
-                acc += B[symtri(r, s)] * c[s + j * NRA];
+                if (mnz<MC>(s + j * NRA)) acc += B[symtri(r, s)] * c[s + j * NRA];
             bc[r + j * NRA] = acc;
         }
 #pragma unroll
@@ -122,7 +131,7 @@ __device__ __forceinline__ void add_mul2_tri(double *base, const double *B, cons
             double acc = 0.0;
 #pragma unroll
             for (int s = 0; s < NRA; s++)
-                acc += a[s + i * NRA] * bc[s + j * NRA];
+                if (mnz<MA>(s + i * NRA)) acc += a[s + i * NRA] * bc[s + j * NRA];
             base[i + j * NCA] += acc;
         }
 }
@@ -523,19 +532,19 @@ __global__ void __launch_bounds__(BP_BLOCK, ILQG_BP_MINBLOCKS) k_backpass(Work w
             /* Q-function (back_pass.c:80-131) */
 #pragma unroll
             for (int i = 0; i < NU; i++) Qu[i] = D.cu[i];
-            add_mul_vec<NX, NU>(Qu, Vx, D.fu);
+            add_mul_vec<NX, NU, typename P::Mask_fu>(Qu, Vx, D.fu);
 #pragma unroll
             for (int i = 0; i < NX; i++) Qx[i] = D.cx[i];
-            add_mul_vec<NX, NX>(Qx, Vx, D.fx);
+            add_mul_vec<NX, NX, typename P::Mask_fx>(Qx, Vx, D.fx);
 #pragma unroll
             for (int i = 0; i < NQXU; i++) Qxu[i] = D.cxu[i];
-            add_mul2_tri<NX, NX, NU>(Qxu, Vxx, D.fx, D.fu);
+            add_mul2_tri<NX, NX, NU, typename P::Mask_fx, typename P::Mask_fu>(Qxu, Vxx, D.fx, D.fu);
 #pragma unroll
             for (int i = 0; i < NQUU; i++) Quu[i] = D.cuu[i];
-            add_square_tri<NX, NU>(Quu, Vxx, D.fu);
+            add_square_tri<NX, NU, typename P::Mask_fu>(Quu, Vxx, D.fu);
 #pragma unroll
             for (int i = 0; i < NQXX; i++) Qxx[i] = D.cxx[i];
-            add_square_tri<NX, NX>(Qxx, Vxx, D.fx);
+            add_square_tri<NX, NX, typename P::Mask_fx>(Qxx, Vxx, D.fx);
             if (FULL) {
                 double v2[P::NV2];
 #pragma unroll
@@ -1069,7 +1078,7 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
  * first lines of iLQG(), iLQG.c:227-237).  MODE 1 = backtracking line search + accept/reject (line_search.c:33-78,
  * iLQG.c:306-361).
  * ===================================================================================================================== */
-template <class P>
+template <class P, bool STORE = true>
 __device__ __forceinline__ bool rollout(const Work &w, const ParamBlock<P> &pb, int b, int from, int to, double alpha,
                                         double w_pen_l, double w_pen_f, double &csum)
 {
@@ -1104,7 +1113,7 @@ __device__ __forceinline__ bool rollout(const Work &w, const ParamBlock<P> &pb, 
         for (int i = 0; i < P::N_MU_R; i++) mu[i] = w.muR[((size_t)k * P::N_MU_R + i) * Bp + b];
         double c;
         const bool ok = P::step(x, u, pb.v, w.pk, k, T, w_pen_l, mu, xn, c);
-        st_rec<RXU>(w.XU[to] + ((size_t)k * Bp + b) * RXU, xu);
+        if (STORE) st_rec<RXU>(w.XU[to] + ((size_t)k * Bp + b) * RXU, xu);
         if (!ok) return false;
         csum += c;
 #pragma unroll
@@ -1112,7 +1121,7 @@ __device__ __forceinline__ bool rollout(const Work &w, const ParamBlock<P> &pb, 
     }
 #pragma unroll
     for (int j = 0; j < NU; j++) u[j] = 0.0;
-    st_rec<RXU>(w.XU[to] + ((size_t)T * Bp + b) * RXU, xu);
+    if (STORE) st_rec<RXU>(w.XU[to] + ((size_t)T * Bp + b) * RXU, xu);
 #pragma unroll
     for (int i = 0; i < P::N_MU_F; i++) mu[i] = w.muF[(size_t)i * Bp + b];
     double c;
@@ -1249,6 +1258,39 @@ __global__ void __launch_bounds__(BP_BLOCK) k_rollout_only(Work w, ParamBlock<P>
     w.result[b] = ok ? 1 : 0;
 }
 
+/* accept / reject bookkeeping of one problem once its line search is decided (iLQG.c:311-361) */
+__device__ __forceinline__ void ls_decide(const Work &w, const Opts &o, int b, int iter, int cur, bool accepted, int alpha_idx,
+                                          double cnew, double dcost, double w_pen_l, double w_pen_f)
+{
+    const size_t Bp = w.Bp;
+    double lambda = w.lambda[b], dlambda = w.dlambda[b];
+    if (w.tr_alpha) w.tr_alpha[(size_t)iter * Bp + b] = alpha_idx;
+    if (w.tr_newcost) w.tr_newcost[(size_t)iter * Bp + b] = cnew;
+    int post = POST_NONE;
+    if (accepted) { /* iLQG.c:311-338 */
+        lower_lambda(o, lambda, dlambda);
+        w.cur[b] = cur ^ 1;
+        w.cost[b] = cnew;
+        w.new_deriv[b] = 1;
+        if (dcost < o.tolFun)
+            finish(w, b, iter, 1);
+        else
+            post = POST_MULT;
+    } else { /* iLQG.c:340-361 */
+        raise_lambda(o, lambda, dlambda);
+        if (o.w_pen_fact2 > 1.0) {
+            w.w_pen_l[b] = dmin(o.w_pen_max_l, w_pen_l * o.w_pen_fact2);
+            w.w_pen_f[b] = dmin(o.w_pen_max_f, w_pen_f * o.w_pen_fact2);
+            post = POST_COST;
+        }
+        if (lambda > o.lambdaMax)
+            finish(w, b, iter, 1); /* backPassDone is set and iter < max_iter: the reference returns 1 here */
+    }
+    w.post_mode[b] = post;
+    w.lambda[b] = lambda;
+    w.dlambda[b] = dlambda;
+}
+
 /* K3: line search, one ROUND per launch.  Round r rolls out alpha[r] for every problem that has not accepted a step
  * yet (line_search.c:37-60 tries the alphas in order and takes the first with z > zMin).  Round 0 runs over all
  * running problems with lane == problem; every later round runs over the compacted list of problems the previous
@@ -1293,32 +1335,7 @@ k_ls_round(Work w, Opts o, ParamBlock<P> pb, int iter, int round)
         w.dcost[b] = dcost;
         w.expected[b] = expected;
         if (accepted || round == o.n_alpha - 1) {
-            double lambda = w.lambda[b], dlambda = w.dlambda[b];
-            if (w.tr_alpha) w.tr_alpha[(size_t)iter * Bp + b] = accepted ? round + 1 : o.n_alpha + 1;
-            if (w.tr_newcost) w.tr_newcost[(size_t)iter * Bp + b] = cnew;
-            int post = POST_NONE;
-            if (accepted) { /* iLQG.c:311-338 */
-                lower_lambda(o, lambda, dlambda);
-                w.cur[b] = cur ^ 1;
-                w.cost[b] = cnew;
-                w.new_deriv[b] = 1;
-                if (dcost < o.tolFun)
-                    finish(w, b, iter, 1);
-                else
-                    post = POST_MULT;
-            } else { /* iLQG.c:340-361 */
-                raise_lambda(o, lambda, dlambda);
-                if (o.w_pen_fact2 > 1.0) {
-                    w.w_pen_l[b] = dmin(o.w_pen_max_l, w_pen_l * o.w_pen_fact2);
-                    w.w_pen_f[b] = dmin(o.w_pen_max_f, w_pen_f * o.w_pen_fact2);
-                    post = POST_COST;
-                }
-                if (lambda > o.lambdaMax)
-                    finish(w, b, iter, 1); /* backPassDone is set and iter < max_iter: the reference returns 1 here */
-            }
-            w.post_mode[b] = post;
-            w.lambda[b] = lambda;
-            w.dlambda[b] = dlambda;
+            ls_decide(w, o, b, iter, cur, accepted, accepted ? round + 1 : o.n_alpha + 1, cnew, dcost, w_pen_l, w_pen_f);
         } else {
             undecided = true;
         }
@@ -1341,8 +1358,74 @@ k_ls_round(Work w, Opts o, ParamBlock<P> pb, int iter, int round)
         s_base = tot ? atomicAdd(&w.ls_count[round + 1], tot) : 0;
     }
     __syncthreads();
-    if (undecided)
+    if (undecided) {
         w.ls_list[(round + 1) & 1][s_base + s_warp[wid] + __popc(ballot & ((1u << lane) - 1u))] = b;
+        w.ls_mask[b] = 0;
+    }
+}
+
+/* K3 tail (small batches, where a launch is bound by the latency of ONE 500-step rollout, not by throughput): after
+ * `from` sequential rounds, all remaining alphas of every undecided problem are rolled out AT ONCE, one lane per
+ * (problem, alpha), without storing trajectories; k_ls_commit then replays the reference's sequential decision over
+ * the recorded costs (first alpha with z > zMin wins, line_search.c:37-60) and re-runs only the winning rollout with
+ * stores.  The line search then costs from + 2 rollout latencies instead of n_alpha; results are bit-identical. */
+template <class P>
+__global__ void __launch_bounds__(BP_BLOCK, ILQG_LS_MINBLOCKS) k_ls_tail(Work w, Opts o, ParamBlock<P> pb, int from)
+{
+    const int nrem = o.n_alpha - from;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = tid / nrem, a = from + tid % nrem;
+    if (i >= w.ls_count[from]) return;
+    const int b = w.ls_list[from & 1][i];
+    const int cur = w.cur[b];
+    const double alpha = o.alpha[a];
+    double cnew;
+    const bool ok = rollout<P, false>(w, pb, b, cur, cur ^ 1, alpha, w.w_pen_l[b], w.w_pen_f[b], cnew);
+    w.ls_cnew[(size_t)a * w.Bp + b] = cnew;
+    if (ok) {
+        const double dcost = w.cost[b] - cnew;
+        const double expected = -alpha * (w.dV0[b] + alpha * w.dV1[b]);
+        const double z = (expected > 0) ? dcost / expected : 0.0;
+        atomicOr(&w.ls_mask[b], (1 << a) | ((z > o.zMin) ? (1 << (16 + a)) : 0));   /* low half: rollout ok, high half: accepted */
+    }
+}
+
+template <class P>
+__global__ void __launch_bounds__(BP_BLOCK, ILQG_LS_MINBLOCKS) k_ls_commit(Work w, Opts o, ParamBlock<P> pb, int iter, int from)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= w.ls_count[from]) return;
+    const int b = w.ls_list[from & 1][tid];
+    const size_t Bp = w.Bp;
+    const int cur = w.cur[b];
+    const int mask = w.ls_mask[b];
+    const double cost = w.cost[b], dV0 = w.dV0[b], dV1 = w.dV1[b];
+    double w_pen_l = w.w_pen_l[b], w_pen_f = w.w_pen_f[b];
+    double cnew = w.new_cost[b], dcost = w.dcost[b], expected = w.expected[b];
+    int win = -1;
+    for (int a = from; a < o.n_alpha; a++) { /* the sequential semantics over the recorded rollouts */
+        cnew = w.ls_cnew[(size_t)a * Bp + b];
+        if (mask & (1 << a)) {
+            const double alpha = o.alpha[a];
+            dcost = cost - cnew;
+            expected = -alpha * (dV0 + alpha * dV1);
+            if (w.tr_z) w.tr_z[(size_t)iter * Bp + b] = (expected > 0) ? dcost / expected : 0.0;
+        }
+        if (mask & (1 << (16 + a))) {
+            win = a;
+            break;
+        }
+    }
+    w.n_roll[b] += (o.n_alpha - from) + (win >= 0 ? 1 : 0);
+    if (win >= 0) {
+        double c2;
+        rollout<P, true>(w, pb, b, cur, cur ^ 1, o.alpha[win], w_pen_l, w_pen_f, c2); /* same arithmetic -> same cost */
+        cnew = c2;
+    }
+    w.new_cost[b] = cnew;
+    w.dcost[b] = dcost;
+    w.expected[b] = expected;
+    ls_decide(w, o, b, iter, cur, win >= 0, win >= 0 ? win + 1 : o.n_alpha + 1, cnew, dcost, w_pen_l, w_pen_f);
 }
 
 /* K5: update_multipliers(o, 0) and the cost-only pass that follows an accepted step, or the cost-only pass after a

@@ -13,6 +13,8 @@ typedef struct ilqg_opts {
     double tolGrad, tolFun, tolConstraint, zMin;
     double w_pen_init_l, w_pen_init_f, w_pen_max_l, w_pen_max_f, w_pen_fact1, w_pen_fact2;
     int regType, max_iter;
+    int ls_tail_from;   /* line search: rounds [0, ls_tail_from) run one alpha per launch, the remaining alphas all at once;
+                           >= n_alpha: purely sequential rounds (large batches) */
 } ilqg_opts;
 
 /* device workspace of one batch; all arrays are [..][Bp] with the problem index fastest */
@@ -28,6 +30,8 @@ typedef struct ilqg_work {
     double *cost, *new_cost, *dcost, *expected, *lambda, *dlambda, *g_norm, *dV0, *dV1, *w_pen_l, *w_pen_f;
     int *cur, *status, *new_deriv, *deriv_fail, *iterations, *result, *n_ls, *n_bp, *bp_done, *post_mode;
     int *ls_list[2], *ls_count; /* line search: compacted lists of undecided problems (ping-pong), per-round counts */
+    double *ls_cnew;            /* [MAX_ALPHA][Bp] rollout cost per alpha (parallel tail of the line search) */
+    int *ls_mask;               /* [Bp] bit a: rollout of alpha a finite; bit 16+a: alpha a acceptable */
     int *n_dv, *n_roll;        /* work counters: derivative sweeps consumed, rollouts tried (bench roofline accounting) */
     /* optional traces for parity tests (null when disabled) */
     double *tr_lambda, *tr_newcost, *tr_z; /* [max_iter][Bp]: lambda at the line search, last rollout cost, last z */

@@ -333,6 +333,14 @@ def emit_device(m, struct_name) -> str:
     o.append("    __device__ __forceinline__ static void add2_Qxx(const double *Vx, const double *v2, const double *p, double *Qxx) {\n        (void)Vx; (void)v2; (void)p; (void)Qxx;")
     pre, body = contraction(m.fxx, v2_pos, m.nqxx, "Qxx"); o.append(pre); o.append(body); o.append("    }\n")
 
+    # ---- structural-zero masks of the first-order blocks (compile-time): the lane-per-problem backward pass skips
+    #      multiplications by entries that are identically zero for this problem -------------------------------------------
+    for key, entries in blocks1:
+        ent = sorted(entries, key=lambda e: e.idx)
+        bits = ", ".join("false" if (not e.time_var and e.expr == 0) else "true" for e in ent)
+        o.append("    struct Mask_%s { __host__ __device__ static constexpr bool nz(int i) { constexpr bool t[] = {%s}; return t[i]; } };" % (key, bits))
+    o.append("")
+
     # ---- data-driven forms for the warp-cooperative backward pass ------------------------------------------------------
     # (a) destination of every stored time-varying entry inside the dense per-step record (struct Dense in
     #     ilqg_kernels.cuh: fx fu cx cxx cu cuu cxu lower upper lower_sign upper_sign lower_hx upper_hx, contiguous doubles)
