@@ -1,0 +1,63 @@
+"""`.mac` front end (gen/ilqg_gen/macfile.py): the reference's own example files parse into the same models as the
+hand-written problem modules, and a problem file written for this repo goes through the whole generator."""
+import os
+import subprocess
+import tempfile
+
+import pytest
+import sympy as sp
+
+from ilqg_gen.emit_c import emit_func_c, emit_problem_h
+from ilqg_gen.emit_cuda import emit_device
+from ilqg_gen.lower import lower
+from ilqg_gen.macfile import load_mac
+from ilqg_gen.problems import REGISTRY
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference/examples"
+
+
+def _same(a, b):
+    """equal up to symbol identity (assumptions differ between the two front ends)"""
+    ra = a.xreplace({s: sp.Symbol(s.name) for s in a.free_symbols})
+    rb = b.xreplace({s: sp.Symbol(s.name) for s in b.free_symbols})
+    return sp.simplify(ra - rb) == 0
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference tree not present on this machine")
+@pytest.mark.parametrize("mac,mod", [("CarParking/optDefCar.mac", "car"), ("Brachistochrone/optDefBrachi.mac", "brachi"),
+                                     ("Brachistochrone/optDefBrachi_hli.mac", "brachi_hli")])
+def test_reference_examples_parse_to_the_same_model(mac, mod):
+    a, b = lower(load_mac(os.path.join(REF, mac))), lower(REGISTRY[mod]())
+    assert [d.name for d in a.params] == [d.name for d in b.params] and [d.size for d in a.params] == [d.size for d in b.params]
+    assert [s.name for s in a.x] == [s.name for s in b.x] and [s.name for s in a.u] == [s.name for s in b.u]
+    assert [x.name for x in a.aux] == [x.name for x in b.aux] and a.n_mu == b.n_mu
+    assert all(_same(p, q) for p, q in zip(a.f, b.f))
+    for p, q in zip(a.aux, b.aux):
+        assert _same(p.expr, q.expr), p.name
+    assert _same(a.L, b.L) and _same(a.F, b.F)
+    assert [(h["input"], h["sign"]) for h in a.h] == [(h["input"], h["sign"]) for h in b.h]
+    assert all(_same(h1["limit"], h2["limit"]) for h1, h2 in zip(a.h, b.h))
+
+
+def test_own_mac_file_generates_and_compiles():
+    P = load_mac(os.path.join(ROOT, "tests", "data", "pendulum.mac"), "Pendulum")
+    m = lower(P)
+    assert (m.nx, m.nu) == (2, 1) and [a.name for a in m.aux][:1] == ["acc"]
+    assert [d.name for d in m.params] == ["b", "cu", "dt", "g", "l", "m", "q", "qf", "thg", "tmax"]
+    assert [(h["input"], h["sign"]) for h in m.h] == [(0, -1), (0, 1)]        # ascending h index: lower bound first
+    assert m.n_mu == {"fe": 1, "fi": 0, "le": 0, "li": 0}
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "iLQG_problem.h"), "w").write(emit_problem_h(m))
+        open(os.path.join(d, "iLQG_func.c"), "w").write(emit_func_c(m))
+        open(os.path.join(d, "pendulum_device.cuh"), "w").write(emit_device(m, "ProbPendulum"))
+        inc = ["-I" + d, "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "ddp-generator_b200", "csrc")]
+        subprocess.run(["gcc", "-std=gnu11", "-O1", "-ffp-contract=off", "-w", "-DFULL_DDP=1", "-DPRNT=printf", *inc, "-c",
+                        os.path.join(d, "iLQG_func.c"), "-o", os.path.join(d, "f.o")], check=True)
+        cu = os.path.join(d, "t.cu")
+        open(cu, "w").write('#include "ilqg_kernels.cuh"\n#include "pendulum_device.cuh"\n'
+                            'template __global__ void ilqg::k_derivs<ProbPendulum, true>(ilqg_work, ilqg::ParamBlock<ProbPendulum>);\n'
+                            'template __global__ void ilqg::k_backpass<ProbPendulum, true>(ilqg_work, ilqg_opts, ilqg::ParamBlock<ProbPendulum>, int);\n'
+                            'template __global__ void ilqg::k_ls_round<ProbPendulum>(ilqg_work, ilqg_opts, ilqg::ParamBlock<ProbPendulum>, int, int);\n')
+        subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-fmad=false", "-diag-suppress", "550,177,20281",
+                        *inc, "-c", cu, "-o", os.path.join(d, "t.o")], check=True)
