@@ -6,6 +6,6 @@ import ilqg_b200
 from ilqg_b200 import workloads as W
 B, it = int(sys.argv[1]), int(sys.argv[2])
 x0, u0 = W.car_batch(B)
-s = ilqg_b200.BatchSolver("car", 0, B, 500)
+s = ilqg_b200.BatchSolver("car", 0, B, 500, chunks=int(os.environ.get("CHUNKS", "0")))
 s.set_params(W.CAR_PARAMS); s.set_options({"max_iter": it}); s.upload(x0, u0); s.run(); s.sync()
 print("done", s.download(False)["n_linesearch"].sum())
