@@ -143,34 +143,91 @@ DM_HD int dm_rem_pio2(double x, double *y0, double *y1)
     return n & 3;
 }
 
+/* sin and cos of one argument, sharing the range reduction.  Straight-line code: both polynomial kernels are always
+ * evaluated and the results picked by select, so lanes of a warp never diverge on the quadrant and independent calls
+ * can be interleaved by the compiler (only the rare second/third reduction stage is a branch).  Every selected value
+ * is computed by exactly the operations of the classic branching formulation, so results are bit-identical to it
+ * (pinned by tests/golden/dm_math.npz). */
+DM_HD void dm_sincos(double x, double *sn, double *cs)
+{
+    const double invpio2 = 6.36619772367581382433e-01;
+    const double p1 = 1.57079632673412561417e+00, p1t = 6.07710050650619224932e-11;
+    const double p2 = 6.07710050630396597660e-11, p2t = 2.02226624879595063154e-21;
+    const double p3 = 2.02226624871116645580e-21, p3t = 8.47842766036889956997e-32;
+    const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03,
+                 S3 = -1.98412698298579493134e-04, S4 = 2.75573137070700676789e-06,
+                 S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+    const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03,
+                 C3 = 2.48015872894767294178e-05, C4 = -2.75573143513906633035e-07,
+                 C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+    const uint32_t ix = dm_hi_abs(x);
+    const int small = (ix <= 0x3fe921fbu);      /* |x| <= ~pi/4: no reduction */
+    const int bad = (ix >= 0x413921fbu);        /* |x| >= 2^20*pi/2, inf or nan */
+    const int neg = ((int64_t)dm_to_bits(x) < 0);
+    const double ax = dm_from_bits(dm_to_bits(x) & 0x7fffffffffffffffull);
+    const int n = (small | bad) ? 0 : (int)(ax * invpio2 + 0.5);
+    const double fn = (double)n;
+    double r = ax - fn * p1;
+    double w = fn * p1t;
+    const int j = (int)(ix >> 20);
+    double h = r - w;
+    int i = j - (int)((dm_hi_abs(h) >> 20) & 0x7ffu);
+    if (i > 16 && !bad) { /* second stage (rare: heavy cancellation) */
+        double t = r;
+        w = fn * p2;
+        r = t - w;
+        w = fn * p2t - ((t - r) - w);
+        h = r - w;
+        i = j - (int)((dm_hi_abs(h) >> 20) & 0x7ffu);
+        if (i > 49) { /* third stage */
+            t = r;
+            w = fn * p3;
+            r = t - w;
+            w = fn * p3t - ((t - r) - w);
+            h = r - w;
+        }
+    }
+    const double l = (r - h) - w;
+    const double y0 = small ? x : (neg ? -h : h);
+    const double y1 = small ? 0.0 : (neg ? -l : l);
+    const int q = (neg ? -n : n) & 3;
+    /* sine kernel, both published variants (with / without tail), selected like the branching code does */
+    const double z = y0 * y0;
+    const double v = z * y0;
+    const double rs = S2 + z * (S3 + z * (S4 + z * (S5 + z * S6)));
+    const double ks_notail = y0 + v * (S1 + z * rs);
+    const double ks_tail = y0 - ((z * (0.5 * y1 - v * rs) - y1) - v * S1);
+    const double ks = small ? ks_notail : ks_tail;
+    /* cosine kernel */
+    const uint32_t iy = dm_hi_abs(y0);
+    const double rc = z * (C1 + z * (C2 + z * (C3 + z * (C4 + z * (C5 + z * C6)))));
+    const double xy = z * rc - y0 * y1;
+    const double kc_small = 1.0 - (0.5 * z - xy);
+    const double qx = (iy > 0x3fe90000u) ? 0.28125 : dm_from_bits((uint64_t)(uint32_t)(iy - 0x00200000u) << 32);
+    const double hz = 0.5 * z - qx;
+    const double kc_big = (1.0 - qx) - (hz - xy);
+    const double kc = (iy < 0x3fd33333u) ? kc_small : kc_big;
+    /* quadrant */
+    const double s_sel = (q & 1) ? kc : ks;
+    const double c_sel = (q & 1) ? ks : kc;
+    const double s_val = (q & 2) ? -s_sel : s_sel;
+    const double c_val = ((q + 1) & 2) ? -c_sel : c_sel;
+    *sn = bad ? dm_nan() : s_val;
+    *cs = bad ? dm_nan() : c_val;
+}
+
 DM_HD double dm_sin(double x)
 {
-    double y0, y1;
-    int q = dm_rem_pio2(x, &y0, &y1);
-    if (q < 0)
-        return dm_nan();
-    int tail = (dm_hi_abs(x) > 0x3fe921fbu);
-    switch (q) {
-    case 0: return dm_ksin(y0, y1, tail);
-    case 1: return dm_kcos(y0, y1);
-    case 2: return -dm_ksin(y0, y1, tail);
-    default: return -dm_kcos(y0, y1);
-    }
+    double s, c;
+    dm_sincos(x, &s, &c);
+    return s;
 }
 
 DM_HD double dm_cos(double x)
 {
-    double y0, y1;
-    int q = dm_rem_pio2(x, &y0, &y1);
-    if (q < 0)
-        return dm_nan();
-    int tail = (dm_hi_abs(x) > 0x3fe921fbu);
-    switch (q) {
-    case 0: return dm_kcos(y0, y1);
-    case 1: return -dm_ksin(y0, y1, tail);
-    case 2: return -dm_kcos(y0, y1);
-    default: return dm_ksin(y0, y1, tail);
-    }
+    double s, c;
+    dm_sincos(x, &s, &c);
+    return c;
 }
 
 DM_HD double dm_tan(double x) { return dm_sin(x) / dm_cos(x); }

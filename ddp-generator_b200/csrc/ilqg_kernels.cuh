@@ -730,11 +730,13 @@ constexpr int CW_WARPS = 4;
 
 template <class P> struct CoopWS {
     Dense<P> D;
-    double Vx[P::NX], Vxx[P::NQXX], Qx[P::NX], Qu[P::NU], Qxx[P::NQXX], Quu[P::NQUU], Qxu[P::NQXU], QuuF[P::NQUU], Qxu_reg[P::NQXU];
+    double Vx[P::NX], VxxF[P::NX * P::NX], QuuS[P::NU * P::NU];   /* full symmetric copies: plain row*N+col addressing */
+    double Qx[P::NX], Qu[P::NU], Qxx[P::NQXX], Quu[P::NQUU], Qxu[P::NQXU], QuuF[P::NQUU], Qxu_reg[P::NQXU];
     double ba[P::NX * P::NX], bc[P::NX * P::NU], bl[P::NU * P::NX], bv[P::NU];
     double Lk[P::NU * P::NX], lk[P::NU], invH[P::NQUU];
     double v2[P::NV2], c2[P::NC2];
     int clamped[P::NU];
+    unsigned char tri_r[P::NQXX], tri_c[P::NQXX];   /* packed upper-triangle index -> (row, col) */
 };
 
 __device__ __forceinline__ void tri_rc(int e, int &r, int &c)
@@ -775,6 +777,12 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
         P::consts(pb.v, ws.D);
         if (FULL) P::consts2(pb.v, ws.c2);
     }
+    for (int e = lane; e < NQXX; e += 32) {
+        int r, c;
+        tri_rc(e, r, c);
+        ws.tri_r[e] = (unsigned char)r;
+        ws.tri_c[e] = (unsigned char)c;
+    }
     __syncwarp();
 
     double dV0 = 0.0, dV1 = 0.0, g_sum = 0.0;
@@ -783,7 +791,11 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
     while (!done) {
         n_bp++;
         for (int e = lane; e < NX; e += 32) ws.Vx[e] = w.FD[(size_t)e * Bp + b];
-        for (int e = lane; e < NQXX; e += 32) ws.Vxx[e] = w.FD[(size_t)(NX + e) * Bp + b];
+        for (int e = lane; e < NQXX; e += 32) {
+            const double v = w.FD[(size_t)(NX + e) * Bp + b];
+            ws.VxxF[ws.tri_r[e] * NX + ws.tri_c[e]] = v;
+            ws.VxxF[ws.tri_c[e] * NX + ws.tri_r[e]] = v;
+        }
         dV0 = 0.0;
         dV1 = 0.0;
         g_sum = 0.0;
@@ -806,24 +818,28 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
             /* ---- phase 1: Qu, Qx, Vxx*fu, Vxx*fx (back_pass.c:80-92, matMult.c first halves) ---- */
             for (int e = lane; e < NU; e += 32) {
                 double acc = ws.D.cu[e];
+#pragma unroll
                 for (int r = 0; r < NX; r++) acc += ws.Vx[r] * ws.D.fu[r + e * NX];
                 ws.Qu[e] = acc;
             }
             for (int e = lane; e < NX; e += 32) {
                 double acc = ws.D.cx[e];
+#pragma unroll
                 for (int r = 0; r < NX; r++) acc += ws.Vx[r] * ws.D.fx[r + e * NX];
                 ws.Qx[e] = acc;
             }
             for (int e = lane; e < NX * NU; e += 32) {
                 const int r = e % NX, j = e / NX;
                 double acc = 0.0;
-                for (int s = 0; s < NX; s++) acc += ws.Vxx[symtri(r, s)] * ws.D.fu[s + j * NX];
+#pragma unroll
+                for (int s = 0; s < NX; s++) acc += ws.VxxF[r * NX + s] * ws.D.fu[s + j * NX];
                 ws.bc[e] = acc;
             }
             for (int e = lane; e < NX * NX; e += 32) {
                 const int r = e % NX, c = e / NX;
                 double acc = 0.0;
-                for (int s = 0; s < NX; s++) acc += ws.Vxx[symtri(r, s)] * ws.D.fx[s + c * NX];
+#pragma unroll
+                for (int s = 0; s < NX; s++) acc += ws.VxxF[r * NX + s] * ws.D.fx[s + c * NX];
                 ws.ba[e] = acc;
             }
             __syncwarp();
@@ -831,6 +847,7 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
             for (int e = lane; e < NQXU; e += 32) {
                 const int i = e % NX, j = e / NX;
                 double acc = 0.0;
+#pragma unroll
                 for (int s = 0; s < NX; s++) acc += ws.D.fx[s + i * NX] * ws.bc[s + j * NX];
                 double q = ws.D.cxu[e] + acc;
                 if (FULL) {
@@ -847,11 +864,12 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
                 ws.Qxu[e] = q;
             }
             for (int e = lane; e < NQUU; e += 32) {
-                int r, c;
-                tri_rc(e, r, c);
+                const int r = ws.tri_r[e], c = ws.tri_c[e];
                 double acc = 0.0;
+#pragma unroll
                 for (int s = 0; s < NX; s++) acc += ws.D.fu[s + r * NX] * ws.bc[s + c * NX];
                 if (r != c) {
+#pragma unroll
                     for (int s = 0; s < NX; s++) acc += ws.D.fu[s + c * NX] * ws.bc[s + r * NX];
                     acc *= 0.5;
                 }
@@ -868,13 +886,16 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
                     }
                 }
                 ws.Quu[e] = q;
+                ws.QuuS[r * NU + c] = q;
+                ws.QuuS[c * NU + r] = q;
             }
             for (int e = lane; e < NQXX; e += 32) {
-                int r, c;
-                tri_rc(e, r, c);
+                const int r = ws.tri_r[e], c = ws.tri_c[e];
                 double acc = 0.0;
+#pragma unroll
                 for (int s = 0; s < NX; s++) acc += ws.D.fx[s + r * NX] * ws.ba[s + c * NX];
                 if (r != c) {
+#pragma unroll
                     for (int s = 0; s < NX; s++) acc += ws.D.fx[s + c * NX] * ws.ba[s + r * NX];
                     acc *= 0.5;
                 }
@@ -991,46 +1012,56 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
             /* ---- phase 3: Quu*l, Quu*L ---- */
             for (int e = lane; e < NU; e += 32) {
                 double acc = 0.0;
-                for (int s = 0; s < NU; s++) acc += ws.Quu[symtri(e, s)] * ws.lk[s];
+#pragma unroll
+                for (int s = 0; s < NU; s++) acc += ws.QuuS[e * NU + s] * ws.lk[s];
                 ws.bv[e] = acc;
             }
             for (int e = lane; e < NU * NX; e += 32) {
                 const int r = e % NU, c = e / NU;
                 double acc = 0.0;
-                for (int s = 0; s < NU; s++) acc += ws.Quu[symtri(r, s)] * ws.Lk[s + c * NU];
+#pragma unroll
+                for (int s = 0; s < NU; s++) acc += ws.QuuS[r * NU + s] * ws.Lk[s + c * NU];
                 ws.bl[e] = acc;
             }
             __syncwarp();
             /* ---- phase 4: value function (back_pass.c:217-241) ---- */
             for (int e = lane; e < NX; e += 32) {
                 double acc = 0.0;
+#pragma unroll
                 for (int s = 0; s < NU; s++) acc += ws.Lk[s + e * NU] * ws.bv[s];
                 double v = ws.Qx[e] + acc;
+#pragma unroll
                 for (int j = 0; j < NU; j++) v += ws.Lk[j + e * NU] * ws.Qu[j];
+#pragma unroll
                 for (int j = 0; j < NU; j++) v += ws.Qxu[e + j * NX] * ws.lk[j];
                 ws.Vx[e] = v;
             }
             for (int e = lane; e < NQXX; e += 32) {
-                int r, c;
-                tri_rc(e, r, c);
+                const int r = ws.tri_r[e], c = ws.tri_c[e];
                 double acc = 0.0;
+#pragma unroll
                 for (int s = 0; s < NU; s++) acc += ws.Lk[s + r * NU] * ws.bl[s + c * NU];
                 if (r != c) {
+#pragma unroll
                     for (int s = 0; s < NU; s++) acc += ws.Lk[s + c * NU] * ws.bl[s + r * NU];
                     acc *= 0.5;
                 }
                 double v = ws.Qxx[e] + acc;
                 if (r == c) {
+#pragma unroll
                     for (int cc = 0; cc < NU; cc++) {
                         double term = ws.Lk[cc + r * NU] * ws.Qxu[r + cc * NX];
                         term *= 2.0;
                         v += term;
                     }
                 } else { /* the reference's loop visits (i=r, j=c) before (i=c, j=r) for r < c */
+#pragma unroll
                     for (int cc = 0; cc < NU; cc++) v += ws.Lk[cc + r * NU] * ws.Qxu[c + cc * NX];
+#pragma unroll
                     for (int cc = 0; cc < NU; cc++) v += ws.Lk[cc + c * NU] * ws.Qxu[r + cc * NX];
                 }
-                ws.Vxx[e] = v;
+                ws.VxxF[r * NX + c] = v;
+                ws.VxxF[c * NX + r] = v;
             }
             /* ---- gradient measure (back_pass.c:244-251) ---- */
             {

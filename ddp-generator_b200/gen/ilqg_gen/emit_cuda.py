@@ -63,6 +63,8 @@ def render(sc: Scope, names, tname, indent="        ", guards=True):
             out.append(f"{indent}{decl}{lhs} = {render_operand(it[2], names)};")
             if it[3] and guards:
                 out.append(f"{indent}ok &= dm_isfinite({lhs});")
+        elif it[0] == "sincos":
+            out.append(f"{indent}double {it[1]}, {it[2]}; dm_sincos({render_operand(it[3], names)}, &{it[1]}, &{it[2]});")
         elif it[0] == "raw":
             out.append(it[1](names, indent))
     return "\n".join(out)

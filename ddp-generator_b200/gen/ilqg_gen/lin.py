@@ -37,6 +37,7 @@ class Scope:
     def __init__(self, prefix="t"):
         self.prefix = prefix
         self.memo = {}
+        self.sincos = {}
         self.items = []   # ("tmp", name, rhs_tokens) | ("out", target, operand, guard) | ("raw", payload)
         self.n = 0
 
@@ -117,6 +118,15 @@ class Scope:
             return self._ipow(self.ref(b), p)
         if isinstance(e, sp.Abs):
             return self._new(("call", "dm_fabs", self.ref(e.args[0])))
+        if e.func in (sp.sin, sp.cos):
+            # sin and cos of one argument come from ONE dm_sincos call (shared range reduction, straight-line code)
+            arg = self.ref(e.args[0])
+            if arg not in self.sincos:
+                sn, cn = f"{self.prefix}{self.n}s", f"{self.prefix}{self.n}c"
+                self.n += 1
+                self.items.append(("sincos", sn, cn, arg))
+                self.sincos[arg] = (("t", sn), ("t", cn))
+            return self.sincos[arg][0 if e.func is sp.sin else 1]
         if e.func in _FUNCS:
             return self._new(("call", _FUNCS[e.func], self.ref(e.args[0])))
         if isinstance(e, sp.Piecewise):
