@@ -301,13 +301,15 @@ def main():
     n_dv = int(K.get_int("n_derivs").sum())
     n_bp = int(K.get_int("n_backpass").sum())
     n_roll = int(K.get_int("n_rollouts").sum())
+    n_tail = int(K.get_int("n_tails").sum())
     K.close()
     NV = S.L.deriv_doubles_per_step
     RXU, RLL = 8 * ((nx + nu + 3) // 4) * 4, 8 * ((nu + nu * nx + 3) // 4) * 4      # record sizes in bytes
     alg = {
         "derivs": n_dv * (T_HOR * (RXU + NV * 8) + (RXU + (nx + nx * (nx + 1) // 2) * 8)),
         "backpass": n_bp * (T_HOR * (NV * 8 + nu * 8 + RLL) + (nx + nx * (nx + 1) // 2) * 8),
-        "linesearch": n_roll * (T_HOR * (RXU + RLL + RXU) + RXU),
+        # a stored rollout reads the nominal records and writes a candidate; a parallel-alpha tail reads the nominal once
+        "linesearch": n_roll * (T_HOR * (RXU + RLL + RXU) + RXU) + n_tail * T_HOR * (RXU + RLL),
     }
     peak, peak_src = measured_peak_hbm()
     kernels = {}

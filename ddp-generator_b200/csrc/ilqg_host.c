@@ -327,6 +327,7 @@ static chunk *ck_create(int device, int batch, int n_hor, int flags, void *strea
         DALLOC(w->ls_mask, int, Bp);
         DALLOC(w->n_dv, int, Bp);
         DALLOC(w->n_roll, int, Bp);
+        DALLOC(w->n_tail, int, Bp);
         ilqgk_memset(w->status, 0, sizeof(int) * Bp, h->stream);
         ilqgk_memset(w->cur, 0, sizeof(int) * Bp, h->stream);
         if (flags & ILQGB_TRACE) {
@@ -720,6 +721,7 @@ static long ck_get_int(chunk *h, const char *f, int *out)
     else if (!strcmp(f, "cur")) scal = w->cur;
     else if (!strcmp(f, "n_derivs")) scal = w->n_dv;
     else if (!strcmp(f, "n_rollouts")) scal = w->n_roll;
+    else if (!strcmp(f, "n_tails")) scal = w->n_tail;
     if (scal) {
         if (ilqgk_d2h(out, scal, sizeof(int) * B, h->stream) || ilqgk_stream_sync(h->stream)) return failk(h);
         return (long)B;

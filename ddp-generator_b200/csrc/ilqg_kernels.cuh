@@ -1232,6 +1232,7 @@ __global__ void __launch_bounds__(BP_BLOCK) k_init(Work w, Opts o, ParamBlock<P>
     w.n_bp[b] = 0;
     w.n_dv[b] = 0;
     w.n_roll[b] = 0;
+    w.n_tail[b] = 0;
     w.bp_done[b] = 0;
     w.deriv_fail[b] = 0;
     w.post_mode[b] = POST_NONE;
@@ -1447,7 +1448,8 @@ __global__ void __launch_bounds__(BP_BLOCK, ILQG_LS_MINBLOCKS) k_ls_commit(Work 
             break;
         }
     }
-    w.n_roll[b] += (o.n_alpha - from) + (win >= 0 ? 1 : 0);
+    w.n_tail[b] += 1;
+    w.n_roll[b] += (win >= 0 ? 1 : 0);
     if (win >= 0) {
         double c2;
         rollout<P, true>(w, pb, b, cur, cur ^ 1, o.alpha[win], w_pen_l, w_pen_f, c2); /* same arithmetic -> same cost */

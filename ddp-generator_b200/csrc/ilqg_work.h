@@ -32,7 +32,8 @@ typedef struct ilqg_work {
     int *ls_list[2], *ls_count; /* line search: compacted lists of undecided problems (ping-pong), per-round counts */
     double *ls_cnew;            /* [MAX_ALPHA][Bp] rollout cost per alpha (parallel tail of the line search) */
     int *ls_mask;               /* [Bp] bit a: rollout of alpha a finite; bit 16+a: alpha a acceptable */
-    int *n_dv, *n_roll;        /* work counters: derivative sweeps consumed, rollouts tried (bench roofline accounting) */
+    int *n_dv, *n_roll, *n_tail; /* work counters (bench roofline accounting): derivative sweeps consumed, rollouts that
+                                  stored a trajectory, parallel-alpha tails (one shared read of the nominal, no stores) */
     /* optional traces for parity tests (null when disabled) */
     double *tr_lambda, *tr_newcost, *tr_z; /* [max_iter][Bp]: lambda at the line search, last rollout cost, last z */
     int *tr_alpha;                  /* [max_iter][Bp] */

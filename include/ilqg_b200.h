@@ -85,7 +85,7 @@ int ilqgb_phase_linesearch(ilqgb_handle *h);
  * "x" "u" (nominal), "l" "L" "v1" (time-varying derivative entries) "v2" "fd" (final cx,cxx) "mu_f" "mu_r";
  * traces (ILQGB_TRACE): "tr_lambda" "tr_newcost" -> [batch][max_iter].  Returns doubles written, <0 on error. */
 long ilqgb_get(ilqgb_handle *h, const char *field, double *out);
-/* "iterations" "result" "status" "n_linesearch" "n_backpass" "n_derivs" "n_rollouts" "cur" -> [batch]; "tr_alpha" -> [batch][max_iter];
+/* "iterations" "result" "status" "n_linesearch" "n_backpass" "n_derivs" "n_rollouts" "n_tails" "cur" -> [batch]; "tr_alpha" -> [batch][max_iter];
  * "tr_clamp" -> [batch][n_hor] (2 bits per input: 0 free, 1 lower, 2 upper; QP return code in bits 16..23) */
 long ilqgb_get_int(ilqgb_handle *h, const char *field, int *out);
 

@@ -22,5 +22,5 @@ for B in [int(a) for a in sys.argv[1:]] or [4096]:
     t = time.perf_counter(); s.run(); s.sync(); dt = time.perf_counter() - t
     out = s.download(False); tm = s.timing()
     nls = out["n_linesearch"].sum()
-    print(f"{PROB} ddp{DDP} B={B} chunks={s.chunks()}: {dt:.3f}s its={nls} -> {nls/dt:.0f} it/s ; kernels {tm}; rollouts {s.get_int('n_rollouts').sum()} backpasses {s.get_int('n_backpass').sum()} derivs {s.get_int('n_derivs').sum()} success {np.bincount(out['success']+1)} iters hist {np.bincount(out['iterations'])[-6:]}")
+    print(f"{PROB} ddp{DDP} B={B} chunks={s.chunks()}: {dt:.3f}s its={nls} -> {nls/dt:.0f} it/s ; kernels {tm}; rollouts {s.get_int('n_rollouts').sum()}+{s.get_int('n_tails').sum()}t backpasses {s.get_int('n_backpass').sum()} derivs {s.get_int('n_derivs').sum()} success {np.bincount(out['success']+1)} iters hist {np.bincount(out['iterations'])[-6:]}")
     s.close()
