@@ -97,10 +97,14 @@ int ilqgk_launch_backpass(const ilqg_work *w, const ilqg_opts *o, const double *
         constexpr size_t smem = sizeof(double) * 2 * bp_fields<P, FULL_DDP != 0>() * BP_BLOCK;
         static bool configured = false;
         if (!configured) {
-            if (check(cudaFuncSetAttribute(k_backpass<P, FULL_DDP != 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return -1;
+            if (check(cudaFuncSetAttribute(k_backpass<P, FULL_DDP != 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return -1;
+            if (check(cudaFuncSetAttribute(k_backpass<P, FULL_DDP != 0, ILQG_BP_MINBLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return -1;
             configured = true;
         }
-        k_backpass<P, FULL_DDP != 0><<<nblk(w->B, BP_BLOCK), BP_BLOCK, smem, (cudaStream_t)stream>>>(*w, *o, make_pb(params), iter);
+        if (o->bp_latency_build)
+            k_backpass<P, FULL_DDP != 0, 1><<<nblk(w->B, BP_BLOCK), BP_BLOCK, smem, (cudaStream_t)stream>>>(*w, *o, make_pb(params), iter);
+        else
+            k_backpass<P, FULL_DDP != 0, ILQG_BP_MINBLOCKS><<<nblk(w->B, BP_BLOCK), BP_BLOCK, smem, (cudaStream_t)stream>>>(*w, *o, make_pb(params), iter);
     }
     return check(cudaGetLastError(), "k_backpass");
 }

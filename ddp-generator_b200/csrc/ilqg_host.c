@@ -35,6 +35,7 @@ struct chunk {
     int owns_stream;
     int iter;              /* pass index of the running problems */
     int ls_tail_from;      /* -1 = choose by batch size */
+    int bp_latency;        /* -1 = choose by batch size */
     int started;
     int trace_cap;         /* max_iter the trace arrays were sized for */
     void **allocs;
@@ -254,6 +255,7 @@ static chunk *ck_create(int device, int batch, int n_hor, int flags, void *strea
     h->T = n_hor;
     h->flags = flags;
     h->ls_tail_from = getenv("ILQG_LS_TAIL_FROM") ? atoi(getenv("ILQG_LS_TAIL_FROM")) : -1;
+    h->bp_latency = getenv("ILQG_BP_LATENCY") ? atoi(getenv("ILQG_BP_LATENCY")) : -1;
     ilqgk_dims(&h->d);
     if (h->d.nkp > 16) {
         fail(NULL, "too many [k]-indexed parameters");
@@ -523,6 +525,7 @@ static int launch_pass(chunk *h, int do_derivs, int do_back, int do_ls)
     }
     if (do_back) {
         p = timing_begin(h, TC_BACKPASS);
+        h->o.bp_latency_build = h->bp_latency >= 0 ? h->bp_latency : (h->B <= 40000);
         if (ilqgk_launch_backpass(&h->w, &h->o, h->params, h->iter, h->stream)) return failk(h);
         h->n_launches++;
         timing_end(h, p);

@@ -470,8 +470,10 @@ __device__ __forceinline__ void bp_issue(const Work &w, double *sm, int k, int s
     cp_async_commit();
 }
 
-template <class P, bool FULL>
-__global__ void __launch_bounds__(BP_BLOCK, ILQG_BP_MINBLOCKS) k_backpass(Work w, Opts o, ParamBlock<P> pb, int iter)
+/* MINB = minimum resident blocks per SM the compiler must allow: 8 caps the kernel at 128 registers (16 warps/SM, the
+   throughput build for large batches); 1 leaves registers free (no spills, shortest per-step latency, small batches) */
+template <class P, bool FULL, int MINB>
+__global__ void __launch_bounds__(BP_BLOCK, MINB) k_backpass(Work w, Opts o, ParamBlock<P> pb, int iter)
 {
     constexpr int NX = P::NX, NU = P::NU, NQXX = P::NQXX, NQUU = P::NQUU, NQXU = P::NQXU;
     constexpr int NF = bp_fields<P, FULL>();

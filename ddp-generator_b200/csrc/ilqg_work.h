@@ -13,6 +13,7 @@ typedef struct ilqg_opts {
     double tolGrad, tolFun, tolConstraint, zMin;
     double w_pen_init_l, w_pen_init_f, w_pen_max_l, w_pen_max_f, w_pen_fact1, w_pen_fact2;
     int regType, max_iter;
+    int bp_latency_build; /* backward pass: 1 = register-unconstrained build (small batches), 0 = 128-register build */
     int ls_tail_from;   /* line search: rounds [0, ls_tail_from) run one alpha per launch, the remaining alphas all at once;
                            >= n_alpha: purely sequential rounds (large batches) */
 } ilqg_opts;
