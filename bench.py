@@ -140,6 +140,33 @@ def cpu_reference_run(n_problems, max_iter, threads, first=0):
     return dict(kind=kind, seconds=dt, iterations=its, value=its / dt, cores=threads, n_problems=n_problems, out=out)
 
 
+def cpu_single_instance():
+    """BASELINE config 1 on the host: one car instance (T=500, max_iter=200) with the reference's single-threaded build
+    and with its experimental -DMULTI_THREADED=1 pipeline (north star: both are reported, neither is the target)."""
+    import oracle_lib
+    from ilqg_b200 import workloads as W
+
+    out = {}
+    x0, u0 = W.car_single()
+    for key, kind, fast in (("single_thread", "reference", True), ("multi_threaded_2", "reference-mt", False)):
+        if not oracle_lib.available(kind, PROBLEM, FULL_DDP, fast):
+            continue
+        s = oracle_lib.OracleLib(kind, PROBLEM, FULL_DDP, fast).solver(T_HOR)
+        s.set_opts({"max_iter": 200})
+        s.set_params(W.CAR_PARAMS)
+        best = None
+        for _ in range(3):
+            s.init(x0, u0)
+            t0 = time.perf_counter()
+            s.solve()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        n = s.scalar("n_linesearch")
+        out[key] = {"iterations_per_s": n / best, "ms_per_iteration": 1e3 * best / n, "iterations": int(n), "final_cost": s.scalar("cost")}
+        s.close()
+    return out
+
+
 def run_reference_arm(args, rank):
     if rank != 0:
         return
@@ -347,7 +374,7 @@ def main():
             same = bool(np.array_equal(r["out"]["cost"], cost_resident[:n])) if first == 0 else None
             cpu = {"value": r["value"], "unit": UNIT, "cores": cores, "kind": r["kind"],
                    "sample": f"first {n} problems of the batch, max_iter={args.steps}, one solver instance per thread, {r['seconds']:.1f} s",
-                   "gpu_costs_bit_identical_on_sample": same}
+                   "gpu_costs_bit_identical_on_sample": same, "config1_single_instance": cpu_single_instance()}
 
     if rank == 0:
         line = {

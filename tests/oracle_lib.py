@@ -12,6 +12,8 @@ _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 
 def lib_path(kind, problem, full_ddp, fast=False):
+    if kind == "reference-mt":      # the reference's -DMULTI_THREADED=1 build (one solve at a time per process)
+        return os.path.join(ROOT, "oracle", "_ref", f"libref_{problem}_ddp{int(full_ddp)}_mt.so")
     d = "_ref" if kind == "reference" else "_build"
     stem = {"reference": "libref", "port": "libport", "b200": "libb200h"}[kind]   # b200 = harness over the GPU drop-in library
     return os.path.join(ROOT, "oracle", d, f"{stem}_{problem}_ddp{int(full_ddp)}{'_fast' if fast else ''}.so")

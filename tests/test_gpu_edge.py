@@ -31,7 +31,8 @@ def test_ragged_batch_sizes(B):
 @pytest.mark.parametrize("opts", [{"max_iter": 0}, {"max_iter": 1}, {"max_iter": 12, "zMin": 0.5}, {"max_iter": 12, "alpha": [1.0, 0.1]},
                                    {"max_iter": 12, "alpha": [0.5]}, {"max_iter": 15, "lambdaInit": 100.0, "lambdaMax": 1000.0},
                                    {"max_iter": 12, "lambdaFactor": 3.0, "lambdaMin": 1e-3, "dlambdaInit": 2.0},
-                                   {"max_iter": 40, "tolFun": 1e-2}, {"max_iter": 40, "tolGrad": 1.0, "lambdaInit": 1e-6}])
+                                   {"max_iter": 40, "tolFun": 1e-2}, {"max_iter": 40, "tolGrad": 1.0, "lambdaInit": 1e-6},
+                                   {"max_iter": 12, "regType": 2}, {"max_iter": 10, "alpha": [1.0, 0.5, 0.25, 0.125, 0.0625, 0.03, 0.01, 0.005, 0.001, 0.0005]}])
 def test_options_follow_reference(opts):
     B, T = 6, 80
     x0, u0 = W.car_batch(B, T=T, seed=31)
