@@ -805,15 +805,53 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
 #pragma unroll
         for (int i = 0; i < NU; i++) lk[i] = 0.0;
         bool failed = false;
+        constexpr int R1 = (P::NV1 + 31) / 32, R2 = (P::NV2 + 31) / 32;
+        double pf1[R1], pf2[R2];
+        {
+            const double *rec = w.V1 + ((size_t)(T - 1) * Bp + b) * P::NV1;
+#pragma unroll
+            for (int t = 0; t < R1; t++) {
+                const int j = lane + 32 * t;
+                pf1[t] = (j < P::NV1) ? rec[j] : 0.0;
+            }
+            const double *rec2 = w.V2 + ((size_t)(T - 1) * Bp + b) * P::NV2;
+#pragma unroll
+            for (int t = 0; t < R2; t++) {
+                const int j = lane + 32 * t;
+                pf2[t] = (FULL && j < P::NV2_USED) ? rec2[j] : 0.0;
+            }
+        }
 
         for (int k = T - 1; k >= 0; k--) {
-            /* ---- load the time-varying entries of step k into the dense record ---- */
-            {
-                const double *rec = w.V1 + ((size_t)k * Bp + b) * P::NV1;
-                for (int j = lane; j < P::NV1; j += 32) Dd[P::v1_dst(j)] = rec[j];
+            /* ---- the time-varying entries of step k were requested one step ahead (registers pf1/pf2, R1/R2 values per
+                    lane); scatter them into the dense record, then request step k-1: its HBM latency hides behind
+                    the arithmetic of this step ---- */
+#pragma unroll
+            for (int t = 0; t < R1; t++) {
+                const int j = lane + 32 * t;
+                if (j < P::NV1) Dd[P::v1_dst(j)] = pf1[t];
+            }
+            if (FULL) {
+#pragma unroll
+                for (int t = 0; t < R2; t++) {
+                    const int j = lane + 32 * t;
+                    if (j < P::NV2_USED) ws.v2[j] = pf2[t];
+                }
+            }
+            if (k > 0) {
+                const double *rec = w.V1 + ((size_t)(k - 1) * Bp + b) * P::NV1;
+#pragma unroll
+                for (int t = 0; t < R1; t++) {
+                    const int j = lane + 32 * t;
+                    if (j < P::NV1) pf1[t] = rec[j];
+                }
                 if (FULL) {
-                    const double *rec2 = w.V2 + ((size_t)k * Bp + b) * P::NV2;
-                    for (int j = lane; j < P::NV2_USED; j += 32) ws.v2[j] = rec2[j];
+                    const double *rec2 = w.V2 + ((size_t)(k - 1) * Bp + b) * P::NV2;
+#pragma unroll
+                    for (int t = 0; t < R2; t++) {
+                        const int j = lane + 32 * t;
+                        if (j < P::NV2_USED) pf2[t] = rec2[j];
+                    }
                 }
             }
             __syncwarp();
@@ -975,7 +1013,7 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
             /* ---- gains (back_pass.c:173-201), one entry per lane; also the control-law record of step k ---- */
             {
                 double *rec = w.LL[cur] + ((size_t)k * Bp + b) * Rec<P>::RLL;
-                for (int e = lane; e < NU * NX; e += 32) {
+            for (int e = lane; e < NU * NX; e += 32) {
                     const int i = e % NU, s = e / NU;
                     double acc = 0.0;
                     if (ws.clamped[i]) {
