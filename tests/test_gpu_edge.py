@@ -116,3 +116,59 @@ def test_properties_at_config3_size():
     # and 64 of them against the oracle
     ora = _oracle("car", 0).solve_batch(x0[:64], u0[:64], W.CAR_PARAMS, {"max_iter": 12.0}, 4, want_traj=True)
     assert np.array_equal(ora["cost"], a["cost"][:64]) and np.array_equal(ora["x"], a["x"][:64])
+
+
+@pytest.mark.parametrize("chunks", [2, 3, 5])
+def test_chunked_streams_match_single_stream(chunks):
+    """A handle split into several concurrent streams (ragged chunk sizes) returns exactly what one stream returns, for
+    every read-back path (download, get, get_int), and matches the oracle."""
+    B, T = 77, 60
+    x0, u0 = W.car_batch(B, T=T, seed=61)
+    opts = {"max_iter": 9}
+    res = []
+    for ch in (1, chunks):
+        s = ilqg_b200.BatchSolver("car", 0, B, T, flags=ilqg_b200.TRACE, chunks=ch)
+        assert 1 <= s.chunks() <= ch and (ch == 1 or s.chunks() > 1)    # chunk sizes are whole warps: fewer chunks may result
+        s.set_options(opts); s.set_params(W.CAR_PARAMS)
+        out = s.solve(x0, u0)
+        out.update(l=s.get("l"), L=s.get("L"), lam=s.get("lambda"), tr=s.get_int("tr_alpha"), nbp=s.get_int("n_backpass"), v1=s.get("v1"))
+        res.append(out)
+        s.close()
+    for k in res[0]:
+        assert np.array_equal(res[0][k], res[1][k]), k
+    ora = _oracle("car", 0).solve_batch(x0, u0, W.CAR_PARAMS, {"max_iter": 9.0}, 2, want_traj=True)
+    assert np.array_equal(res[1]["cost"], ora["cost"]) and np.array_equal(res[1]["x"], ora["x"]) and np.array_equal(res[1]["u"], ora["u"])
+
+
+def test_stepwise_iteration_and_caller_stream():
+    """start + iterate(n) ... + finish on a caller-owned CUDA stream equals solve(); the handle's work is ordered in
+    that stream (events recorded on it bracket the whole solve)."""
+    torch = pytest.importorskip("torch")
+    B, T = 40, 80
+    x0, u0 = W.car_batch(B, T=T, seed=71)
+    ref = ilqg_b200.BatchSolver("car", 0, B, T)
+    ref.set_options({"max_iter": 10}); ref.set_params(W.CAR_PARAMS)
+    want = ref.solve(x0, u0)
+    ref.close()
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        s = ilqg_b200.BatchSolver("car", 0, B, T, stream=st.cuda_stream, chunks=2)
+        s.set_options({"max_iter": 10}); s.set_params(W.CAR_PARAMS)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.upload(x0, u0)
+        e0.record(st)
+        s.start()
+        done = 0
+        while done < 10:
+            n = s.iterate(3)
+            done += n
+            if n == 0:
+                break
+        s.finish()
+        e1.record(st)
+        e1.synchronize()
+        assert e0.elapsed_time(e1) > 0.0
+        got = s.download()
+        s.close()
+    for k in ("cost", "iterations", "n_linesearch", "success", "x", "u"):
+        assert np.array_equal(got[k], want[k]), k
