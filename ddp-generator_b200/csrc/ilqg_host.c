@@ -537,6 +537,7 @@ static int launch_pass(chunk *h, int do_derivs, int do_back, int do_ls)
             /* small batches: one sequential round, then all remaining alphas at once (latency-bound regime);
                large batches: one alpha per launch over the shrinking list of undecided problems (throughput-bound) */
             int from = h->ls_tail_from >= 0 ? h->ls_tail_from : (h->B <= 40000 ? 1 : (h->B <= 100000 ? 3 : h->o.n_alpha));
+            if (from < 1) from = 1;     /* round 0 builds the list of undecided problems the tail works on */
             if (from > h->o.n_alpha || h->o.n_alpha - from < 2) from = h->o.n_alpha;
             h->o.ls_tail_from = from;
             for (r = 0; r < from; r++) {
