@@ -1163,10 +1163,24 @@ __device__ __forceinline__ bool rollout(const Work &w, const ParamBlock<P> &pb, 
 #pragma unroll
     for (int i = 0; i < NX; i++) x[i] = w.x0[(size_t)i * Bp + b];
     csum = 0.0;
+    /* software pipeline: the nominal records of step k+1 are requested before step k is computed, so their HBM / L2
+       latency hides behind the dynamics and cost arithmetic (they do not depend on the rollout's own state) */
+    constexpr bool PF = (RXU + RLL) <= 32;   /* small records only: a second register copy of a large record spills */
+    double nom[RXU], ll[RLL], nom_n[PF ? RXU : 1], ll_n[PF ? RLL : 1];
+    if (PF) {
+        ld_rec<NX + NU>(w.XU[from] + (size_t)b * RXU, nom);
+        if (alpha != 0.0) ld_rec<NU + NU * NX>(w.LL[from] + (size_t)b * RLL, ll);
+    }
     for (int k = 0; k < T; k++) {
-        double nom[RXU], ll[RLL];
-        ld_rec<NX + NU>(w.XU[from] + ((size_t)k * Bp + b) * RXU, nom);
-        if (alpha != 0.0) ld_rec<NU + NU * NX>(w.LL[from] + ((size_t)k * Bp + b) * RLL, ll);
+        if (PF) {
+            if (k + 1 < T) {
+                ld_rec<PF ? NX + NU : 1>(w.XU[from] + ((size_t)(k + 1) * Bp + b) * RXU, nom_n);
+                if (alpha != 0.0) ld_rec<PF ? NU + NU * NX : 1>(w.LL[from] + ((size_t)(k + 1) * Bp + b) * RLL, ll_n);
+            }
+        } else {
+            ld_rec<NX + NU>(w.XU[from] + ((size_t)k * Bp + b) * RXU, nom);
+            if (alpha != 0.0) ld_rec<NU + NU * NX>(w.LL[from] + ((size_t)k * Bp + b) * RLL, ll);
+        }
         if (alpha != 0.0) {
 #pragma unroll
             for (int j = 0; j < NU; j++) u[j] = nom[NX + j] + ll[j] * alpha;
@@ -1189,6 +1203,12 @@ __device__ __forceinline__ bool rollout(const Work &w, const ParamBlock<P> &pb, 
         csum += c;
 #pragma unroll
         for (int i = 0; i < NX; i++) x[i] = xn[i];
+        if (PF) {
+#pragma unroll
+            for (int i = 0; i < (PF ? NX + NU : 0); i++) nom[i] = nom_n[i];
+#pragma unroll
+            for (int i = 0; i < (PF ? NU + NU * NX : 0); i++) ll[i] = ll_n[i];
+        }
     }
 #pragma unroll
     for (int j = 0; j < NU; j++) u[j] = 0.0;
