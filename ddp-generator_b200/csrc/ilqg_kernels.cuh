@@ -164,6 +164,8 @@ __device__ __forceinline__ int box_qp(const double *H, const double *g, const do
     const double min_grad = 1e-8, min_rel_improve = 1e-8, step_dec = 0.6, min_step = 1e-22, armijo = 0.1;
     double U[MP], grad[M], gc[M], search[M], w[M];
     double value, oldvalue = 0.0;
+#pragma unroll
+    for (int i = 0; i < MP; i++) U[i] = 1.0;   /* entries of clamped rows/columns are don't-care but must be defined */
 
 #pragma unroll
     for (int i = 0; i < M; i++) {
@@ -207,24 +209,25 @@ __device__ __forceinline__ int box_qp(const double *H, const double *g, const do
             return 6;
 
         if (iter == 0 || changed) {
-            /* U'U = H(free,free)  (cholesky.c:6-27) */
+            /* U'U = H(free,free)  (cholesky.c:6-27), straight-line: every entry is evaluated and the clamp pattern
+               only SELECTS which terms enter a sum; entries that involve a clamped index hold don't-care values that
+               no later read uses.  Same operations in the same order on the free block, no divergent branches. */
             bool pd = true;
 #pragma unroll
             for (int col = 0; col < M; col++) {
 #pragma unroll
                 for (int row = 0; row <= col; row++) {
-                    if (clamped[col] || clamped[row] || !pd) continue;
+                    const bool act = !clamped[col] && !clamped[row];
                     double dot = 0;
 #pragma unroll
-                    for (int k = 0; k < row; k++)
-                        if (!clamped[k])
-                            dot += U[utri(k, col)] * U[utri(k, row)];
+                    for (int k = 0; k < row; k++) {
+                        const double t = dot + U[utri(k, col)] * U[utri(k, row)];
+                        dot = clamped[k] ? dot : t;
+                    }
                     const double rem = H[utri(row, col)] - dot;
                     if (row == col) {
-                        if (rem <= 0.0)
-                            pd = false;
-                        else
-                            U[utri(row, col)] = sqrt(rem);
+                        if (act && rem <= 0.0) pd = false;
+                        U[utri(row, col)] = sqrt(rem);
                     } else {
                         U[utri(row, col)] = 1.0 / U[utri(row, row)] * rem;
                     }
@@ -232,32 +235,34 @@ __device__ __forceinline__ int box_qp(const double *H, const double *g, const do
             }
             if (!pd)
                 return -1;
-            /* explicit inverse, one unit right-hand side per free column (cholesky.c:51-74) */
+            /* explicit inverse, one unit right-hand side per free column (cholesky.c:51-74), same scheme */
 #pragma unroll
             for (int col = 0; col < M; col++) {
-                if (clamped[col]) continue;
                 w[col] = 1.0;
 #pragma unroll
                 for (int k = col + 1; k < M; k++)
                     w[k] = 0.0;
 #pragma unroll
                 for (int k = col; k < M; k++) {
-                    if (clamped[k]) continue;
+                    double wk = w[k];
 #pragma unroll
-                    for (int i = col; i < k; i++)
-                        if (!clamped[i])
-                            w[k] -= w[i] * U[utri(i, k)];
-                    w[k] /= U[utri(k, k)];
+                    for (int i = col; i < k; i++) {
+                        const double t = wk - w[i] * U[utri(i, k)];
+                        wk = clamped[i] ? wk : t;
+                    }
+                    w[k] = wk / U[utri(k, k)];
                 }
 #pragma unroll
                 for (int k = M - 1; k >= col; k--) {
-                    if (clamped[k]) continue;
+                    double wk = w[k];
 #pragma unroll
-                    for (int i = k + 1; i < M; i++)
-                        if (!clamped[i])
-                            w[k] -= w[i] * U[utri(k, i)];
-                    w[k] /= U[utri(k, k)];
-                    invH[utri(col, k)] = w[k];
+                    for (int i = k + 1; i < M; i++) {
+                        const double t = wk - w[i] * U[utri(k, i)];
+                        wk = clamped[i] ? wk : t;
+                    }
+                    wk = wk / U[utri(k, k)];
+                    w[k] = wk;
+                    invH[utri(col, k)] = wk;
                 }
             }
         }
@@ -267,26 +272,23 @@ __device__ __forceinline__ int box_qp(const double *H, const double *g, const do
         /* search = -Hfree^-1 (g + H x_clamped) - x on the free set (boxQP.c:153-177) */
 #pragma unroll
         for (int i = 0; i < M; i++) {
-            if (clamped[i]) continue;
             double hc = 0.0;
 #pragma unroll
-            for (int j = 0; j < M; j++)
-                if (clamped[j])
-                    hc += H[symtri(i, j)] * x[j];
+            for (int j = 0; j < M; j++) {
+                const double t = hc + H[symtri(i, j)] * x[j];
+                hc = clamped[j] ? t : hc;
+            }
             gc[i] = g[i] + hc;
         }
 #pragma unroll
         for (int i = 0; i < M; i++) {
-            if (clamped[i]) {
-                search[i] = 0.0;
-                continue;
-            }
-            double s = -x[i];
+            double sd = -x[i];
 #pragma unroll
-            for (int j = 0; j < M; j++)
-                if (!clamped[j])
-                    s -= invH[symtri(i, j)] * gc[j];
-            search[i] = s;
+            for (int j = 0; j < M; j++) {
+                const double t = sd - invH[symtri(i, j)] * gc[j];
+                sd = clamped[j] ? sd : t;
+            }
+            search[i] = clamped[i] ? 0.0 : sd;
         }
         double sdotg = 0.0;
 #pragma unroll
