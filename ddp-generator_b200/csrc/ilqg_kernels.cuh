@@ -732,11 +732,13 @@ constexpr int CW_WARPS = 4;
 #define ILQG_CW_MINBLOCKS 4   /* 128 registers: 16 warps per SM; measured best of 1/3/4/5 on the quadrotor */
 #endif
 
+/* leading dimensions of the kernel-private matrices are odd (NX | 1): lanes that walk a column hit distinct banks */
 template <class P> struct CoopWS {
+    static constexpr int LX = P::NX | 1, LU = P::NU | 1;
     Dense<P> D;
-    double Vx[P::NX], VxxF[P::NX * P::NX], QuuS[P::NU * P::NU];   /* full symmetric copies: plain row*N+col addressing */
+    double Vx[P::NX], VxxF[P::NX * LX], QuuS[P::NU * LU];   /* full symmetric copies: plain row*N+col addressing */
     double Qx[P::NX], Qu[P::NU], Qxx[P::NQXX], Quu[P::NQUU], Qxu[P::NQXU], QuuF[P::NQUU], Qxu_reg[P::NQXU];
-    double ba[P::NX * P::NX], bc[P::NX * P::NU], bl[P::NU * P::NX], bv[P::NU];
+    double ba[LX * P::NX], bc[LX * P::NU], bl[LU * P::NX], bv[P::NU];
     double Lk[P::NU * P::NX], lk[P::NU], invH[P::NQUU];
     double v2[P::NV2], c2[P::NC2];
     int clamped[P::NU];
@@ -754,6 +756,7 @@ template <class P, bool FULL>
 __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_warp(Work w, Opts o, ParamBlock<P> pb, int iter)
 {
     constexpr int NX = P::NX, NU = P::NU, NQXX = P::NQXX, NQUU = P::NQUU, NQXU = P::NQXU;
+    constexpr int LX = CoopWS<P>::LX, LU = CoopWS<P>::LU;
     static_assert(sizeof(Dense<P>) == sizeof(double) * P::DENSE_SIZE, "Dense layout must match the generator's table");
     __shared__ CoopWS<P> ws_all[CW_WARPS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -797,8 +800,8 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
         for (int e = lane; e < NX; e += 32) ws.Vx[e] = w.FD[(size_t)e * Bp + b];
         for (int e = lane; e < NQXX; e += 32) {
             const double v = w.FD[(size_t)(NX + e) * Bp + b];
-            ws.VxxF[ws.tri_r[e] * NX + ws.tri_c[e]] = v;
-            ws.VxxF[ws.tri_c[e] * NX + ws.tri_r[e]] = v;
+            ws.VxxF[ws.tri_r[e] * LX + ws.tri_c[e]] = v;
+            ws.VxxF[ws.tri_c[e] * LX + ws.tri_r[e]] = v;
         }
         dV0 = 0.0;
         dV1 = 0.0;
@@ -874,15 +877,15 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
                 const int r = e % NX, j = e / NX;
                 double acc = 0.0;
 #pragma unroll
-                for (int s = 0; s < NX; s++) acc += ws.VxxF[r * NX + s] * ws.D.fu[s + j * NX];
-                ws.bc[e] = acc;
+                for (int s = 0; s < NX; s++) acc += ws.VxxF[r * LX + s] * ws.D.fu[s + j * NX];
+                ws.bc[r + j * LX] = acc;
             }
             for (int e = lane; e < NX * NX; e += 32) {
                 const int r = e % NX, c = e / NX;
                 double acc = 0.0;
 #pragma unroll
-                for (int s = 0; s < NX; s++) acc += ws.VxxF[r * NX + s] * ws.D.fx[s + c * NX];
-                ws.ba[e] = acc;
+                for (int s = 0; s < NX; s++) acc += ws.VxxF[r * LX + s] * ws.D.fx[s + c * NX];
+                ws.ba[r + c * LX] = acc;
             }
             __syncwarp();
             /* ---- phase 2: Qxu, Quu, Qxx (+ FULL_DDP terms; same lane owns the same entry in both) ---- */
@@ -890,7 +893,7 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
                 const int i = e % NX, j = e / NX;
                 double acc = 0.0;
 #pragma unroll
-                for (int s = 0; s < NX; s++) acc += ws.D.fx[s + i * NX] * ws.bc[s + j * NX];
+                for (int s = 0; s < NX; s++) acc += ws.D.fx[s + i * NX] * ws.bc[s + j * LX];
                 double q = ws.D.cxu[e] + acc;
                 if (FULL) {
                     const int t0 = P::s2xu_start(e), t1 = P::s2xu_start(e + 1);
@@ -909,10 +912,10 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
                 const int r = ws.tri_r[e], c = ws.tri_c[e];
                 double acc = 0.0;
 #pragma unroll
-                for (int s = 0; s < NX; s++) acc += ws.D.fu[s + r * NX] * ws.bc[s + c * NX];
+                for (int s = 0; s < NX; s++) acc += ws.D.fu[s + r * NX] * ws.bc[s + c * LX];
                 if (r != c) {
 #pragma unroll
-                    for (int s = 0; s < NX; s++) acc += ws.D.fu[s + c * NX] * ws.bc[s + r * NX];
+                    for (int s = 0; s < NX; s++) acc += ws.D.fu[s + c * NX] * ws.bc[s + r * LX];
                     acc *= 0.5;
                 }
                 double q = ws.D.cuu[e] + acc;
@@ -928,17 +931,17 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
                     }
                 }
                 ws.Quu[e] = q;
-                ws.QuuS[r * NU + c] = q;
-                ws.QuuS[c * NU + r] = q;
+                ws.QuuS[r * LU + c] = q;
+                ws.QuuS[c * LU + r] = q;
             }
             for (int e = lane; e < NQXX; e += 32) {
                 const int r = ws.tri_r[e], c = ws.tri_c[e];
                 double acc = 0.0;
 #pragma unroll
-                for (int s = 0; s < NX; s++) acc += ws.D.fx[s + r * NX] * ws.ba[s + c * NX];
+                for (int s = 0; s < NX; s++) acc += ws.D.fx[s + r * NX] * ws.ba[s + c * LX];
                 if (r != c) {
 #pragma unroll
-                    for (int s = 0; s < NX; s++) acc += ws.D.fx[s + c * NX] * ws.ba[s + r * NX];
+                    for (int s = 0; s < NX; s++) acc += ws.D.fx[s + c * NX] * ws.ba[s + r * LX];
                     acc *= 0.5;
                 }
                 double q = ws.D.cxx[e] + acc;
@@ -1055,15 +1058,15 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
             for (int e = lane; e < NU; e += 32) {
                 double acc = 0.0;
 #pragma unroll
-                for (int s = 0; s < NU; s++) acc += ws.QuuS[e * NU + s] * ws.lk[s];
+                for (int s = 0; s < NU; s++) acc += ws.QuuS[e * LU + s] * ws.lk[s];
                 ws.bv[e] = acc;
             }
             for (int e = lane; e < NU * NX; e += 32) {
                 const int r = e % NU, c = e / NU;
                 double acc = 0.0;
 #pragma unroll
-                for (int s = 0; s < NU; s++) acc += ws.QuuS[r * NU + s] * ws.Lk[s + c * NU];
-                ws.bl[e] = acc;
+                for (int s = 0; s < NU; s++) acc += ws.QuuS[r * LU + s] * ws.Lk[s + c * NU];
+                ws.bl[r + c * LU] = acc;
             }
             __syncwarp();
             /* ---- phase 4: value function (back_pass.c:217-241) ---- */
@@ -1082,10 +1085,10 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
                 const int r = ws.tri_r[e], c = ws.tri_c[e];
                 double acc = 0.0;
 #pragma unroll
-                for (int s = 0; s < NU; s++) acc += ws.Lk[s + r * NU] * ws.bl[s + c * NU];
+                for (int s = 0; s < NU; s++) acc += ws.Lk[s + r * NU] * ws.bl[s + c * LU];
                 if (r != c) {
 #pragma unroll
-                    for (int s = 0; s < NU; s++) acc += ws.Lk[s + c * NU] * ws.bl[s + r * NU];
+                    for (int s = 0; s < NU; s++) acc += ws.Lk[s + c * NU] * ws.bl[s + r * LU];
                     acc *= 0.5;
                 }
                 double v = ws.Qxx[e] + acc;
@@ -1102,8 +1105,8 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
 #pragma unroll
                     for (int cc = 0; cc < NU; cc++) v += ws.Lk[cc + c * NU] * ws.Qxu[r + cc * NX];
                 }
-                ws.VxxF[r * NX + c] = v;
-                ws.VxxF[c * NX + r] = v;
+                ws.VxxF[r * LX + c] = v;
+                ws.VxxF[c * LX + r] = v;
             }
             /* ---- gradient measure (back_pass.c:244-251) ---- */
             {
