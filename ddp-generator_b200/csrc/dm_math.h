@@ -8,7 +8,7 @@
  * `gcc -ffp-contract=off` and `nvcc -fmad=false` they return bit-identical results on host and device.
  *
  * Algorithms: the classic published fdlibm scheme (Cody-Waite three-stage pi/2 reduction, degree-13/14 minimax
- * kernels on [-pi/4, pi/4]; rational approximation for asin).  Accuracy < 1 ulp on the supported range
+ * kernels on [-pi/4, pi/4], evaluated straight-line in dm_sincos; rational approximation for asin/acos).  Accuracy < 1 ulp on the supported range
  * (checked against libm in tests/test_dm_math.py).  |x| >= 2^20*pi/2 for sin/cos returns NaN: the generated
  * NaN/Inf guards then reject the rollout exactly as the reference's guards would for a non-finite value.
  */
@@ -59,89 +59,6 @@ DM_HD double dm_sqrt(double v)
 }
 
 DM_HD double dm_nan(void) { return dm_from_bits(0x7ff8000000000000ull); }
-
-/* polynomial kernels on |x| <= pi/4; (x, y) is a head/tail pair */
-DM_HD double dm_ksin(double x, double y, int have_tail)
-{
-    const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03,
-                 S3 = -1.98412698298579493134e-04, S4 = 2.75573137070700676789e-06,
-                 S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
-    double z = x * x;
-    double v = z * x;
-    double r = S2 + z * (S3 + z * (S4 + z * (S5 + z * S6)));
-    if (!have_tail)
-        return x + v * (S1 + z * r);
-    return x - ((z * (0.5 * y - v * r) - y) - v * S1);
-}
-
-DM_HD double dm_kcos(double x, double y)
-{
-    const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03,
-                 C3 = 2.48015872894767294178e-05, C4 = -2.75573143513906633035e-07,
-                 C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
-    uint32_t ix = dm_hi_abs(x);
-    double z = x * x;
-    double r = z * (C1 + z * (C2 + z * (C3 + z * (C4 + z * (C5 + z * C6)))));
-    if (ix < 0x3fd33333u) /* |x| < 0.3 */
-        return 1.0 - (0.5 * z - (z * r - x * y));
-    double qx;
-    if (ix > 0x3fe90000u) /* |x| > 0.78125 */
-        qx = 0.28125;
-    else
-        qx = dm_from_bits((uint64_t)(ix - 0x00200000u) << 32); /* ~|x|/4, low word cleared */
-    double hz = 0.5 * z - qx;
-    double a = 1.0 - qx;
-    return a - (hz - (z * r - x * y));
-}
-
-/* reduce x to y0+y1 in [-pi/4, pi/4]; returns quadrant (mod 4), or -1 when out of supported range / non-finite */
-DM_HD int dm_rem_pio2(double x, double *y0, double *y1)
-{
-    const double invpio2 = 6.36619772367581382433e-01;
-    const double p1 = 1.57079632673412561417e+00, p1t = 6.07710050650619224932e-11;
-    const double p2 = 6.07710050630396597660e-11, p2t = 2.02226624879595063154e-21;
-    const double p3 = 2.02226624871116645580e-21, p3t = 8.47842766036889956997e-32;
-    uint32_t ix = dm_hi_abs(x);
-    if (ix <= 0x3fe921fbu) { /* |x| <= ~pi/4 */
-        *y0 = x;
-        *y1 = 0.0;
-        return 0;
-    }
-    if (ix >= 0x413921fbu) /* |x| >= 2^20*pi/2, inf or nan */
-        return -1;
-    double ax = dm_from_bits(dm_to_bits(x) & 0x7fffffffffffffffull);
-    int n = (int)(ax * invpio2 + 0.5);
-    double fn = (double)n;
-    double r = ax - fn * p1;
-    double w = fn * p1t;
-    int j = (int)(ix >> 20);
-    double h = r - w;
-    int i = j - (int)((dm_hi_abs(h) >> 20) & 0x7ffu);
-    if (i > 16) { /* second stage */
-        double t = r;
-        w = fn * p2;
-        r = t - w;
-        w = fn * p2t - ((t - r) - w);
-        h = r - w;
-        i = j - (int)((dm_hi_abs(h) >> 20) & 0x7ffu);
-        if (i > 49) { /* third stage */
-            t = r;
-            w = fn * p3;
-            r = t - w;
-            w = fn * p3t - ((t - r) - w);
-            h = r - w;
-        }
-    }
-    double l = (r - h) - w;
-    if ((int64_t)dm_to_bits(x) < 0) {
-        *y0 = -h;
-        *y1 = -l;
-        return (-n) & 3;
-    }
-    *y0 = h;
-    *y1 = l;
-    return n & 3;
-}
 
 /* sin and cos of one argument, sharing the range reduction.  Straight-line code: both polynomial kernels are always
  * evaluated and the results picked by select, so lanes of a warp never diverge on the quadrant and independent calls

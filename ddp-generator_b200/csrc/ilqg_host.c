@@ -573,44 +573,11 @@ static int ck_active(chunk *h)
     return *h->h_counter;
 }
 
-__attribute__((unused)) static int ck_iterate(chunk *h, int n_passes)
-{
-    int done = 0;
-    if (!h->started) return fail(h, "ck_start has not been called");
-    if (ilqgk_set_device(h->device)) return failk(h);
-    while (done < n_passes && h->iter < h->o.max_iter) {
-        if (launch_pass(h, 1, 1, 1)) return -1;
-        h->iter++;
-        done++;
-        if (h->iter % ACTIVE_CHECK_EVERY == 0 && h->iter < h->o.max_iter) {
-            const int a = ck_active(h);
-            if (a < 0) return -1;
-            if (a == 0) break;
-        }
-    }
-    return done;
-}
-
 static int ck_finish(chunk *h)
 {
     if (ilqgk_set_device(h->device)) return failk(h);
     /* problems that are still running after max_iter passes: iLQG.c:365-377 */
     if (h->iter >= h->o.max_iter && ilqgk_launch_finalize(&h->w, h->o.max_iter, h->stream)) return failk(h);
-    return 0;
-}
-
-__attribute__((unused)) static int ck_solve(chunk *h)
-{
-    if (ck_start(h)) return -1;
-    while (h->iter < h->o.max_iter) {
-        const int n = ck_iterate(h, h->o.max_iter - h->iter);
-        if (n < 0) return -1;
-        if (h->iter < h->o.max_iter) { /* stopped early: everything converged */
-            if (ck_active(h) == 0) break;
-        }
-    }
-    /* when the loop ran out of passes, or max_iter == 0, mark the stragglers */
-    if (ilqgk_launch_finalize(&h->w, h->o.max_iter, h->stream)) return failk(h);
     return 0;
 }
 
