@@ -70,41 +70,49 @@ int ilqgk_event_elapsed(void *a, void *b, float *ms) { return check(cudaEventEla
 
 static inline unsigned nblk(int n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
+/* every solver kernel exists for shared parameters and for per-problem parameter sets */
+#define PP_DISPATCH(w_, CALL)          \
+    do {                               \
+        if ((w_)->pp) { constexpr bool PP = true; CALL; } else { constexpr bool PP = false; CALL; } \
+    } while (0)
+
 int ilqgk_launch_init(const ilqg_work *w, const ilqg_opts *o, const double *params, int mode, void *stream)
 {
-    k_init<P><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, make_pb(params), mode);
+    PP_DISPATCH(w, (k_init<P, PP><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, make_pb(params), mode)));
     return check(cudaGetLastError(), "k_init");
 }
 
 int ilqgk_launch_rollout(const ilqg_work *w, const double *params, double alpha, int cost_only, void *stream)
 {
-    k_rollout_only<P><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, make_pb(params), alpha, cost_only);
+    PP_DISPATCH(w, (k_rollout_only<P, PP><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, make_pb(params), alpha, cost_only)));
     return check(cudaGetLastError(), "k_rollout_only");
 }
 
 int ilqgk_launch_derivs(const ilqg_work *w, const double *params, void *stream)
 {
     dim3 grid(nblk(w->B, DV_BLOCK), (unsigned)(w->T + 1));
-    k_derivs<P, FULL_DDP != 0><<<grid, DV_BLOCK, 0, (cudaStream_t)stream>>>(*w, make_pb(params));
+    PP_DISPATCH(w, (k_derivs<P, FULL_DDP != 0, PP><<<grid, DV_BLOCK, 0, (cudaStream_t)stream>>>(*w, make_pb(params))));
     return check(cudaGetLastError(), "k_derivs");
 }
 
 int ilqgk_launch_backpass(const ilqg_work *w, const ilqg_opts *o, const double *params, int iter, void *stream)
 {
     if constexpr (use_coop<P>())
-        k_backpass_warp<P, FULL_DDP != 0><<<nblk(w->B, CW_WARPS), CW_WARPS * 32, 0, (cudaStream_t)stream>>>(*w, *o, make_pb(params), iter);
+        PP_DISPATCH(w, (k_backpass_warp<P, FULL_DDP != 0, PP><<<nblk(w->B, CW_WARPS), CW_WARPS * 32, 0, (cudaStream_t)stream>>>(*w, *o, make_pb(params), iter)));
     else {
         constexpr size_t smem = sizeof(double) * 2 * bp_fields<P, FULL_DDP != 0>() * BP_BLOCK;
         static bool configured = false;
         if (!configured) {
-            if (check(cudaFuncSetAttribute(k_backpass<P, FULL_DDP != 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return -1;
-            if (check(cudaFuncSetAttribute(k_backpass<P, FULL_DDP != 0, ILQG_BP_MINBLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return -1;
+            if (check(cudaFuncSetAttribute(k_backpass<P, FULL_DDP != 0, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return -1;
+            if (check(cudaFuncSetAttribute(k_backpass<P, FULL_DDP != 0, ILQG_BP_MINBLOCKS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return -1;
+            if (check(cudaFuncSetAttribute(k_backpass<P, FULL_DDP != 0, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return -1;
+            if (check(cudaFuncSetAttribute(k_backpass<P, FULL_DDP != 0, ILQG_BP_MINBLOCKS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return -1;
             configured = true;
         }
         if (o->bp_latency_build)
-            k_backpass<P, FULL_DDP != 0, 1><<<nblk(w->B, BP_BLOCK), BP_BLOCK, smem, (cudaStream_t)stream>>>(*w, *o, make_pb(params), iter);
+            PP_DISPATCH(w, (k_backpass<P, FULL_DDP != 0, 1, PP><<<nblk(w->B, BP_BLOCK), BP_BLOCK, smem, (cudaStream_t)stream>>>(*w, *o, make_pb(params), iter)));
         else
-            k_backpass<P, FULL_DDP != 0, ILQG_BP_MINBLOCKS><<<nblk(w->B, BP_BLOCK), BP_BLOCK, smem, (cudaStream_t)stream>>>(*w, *o, make_pb(params), iter);
+            PP_DISPATCH(w, (k_backpass<P, FULL_DDP != 0, ILQG_BP_MINBLOCKS, PP><<<nblk(w->B, BP_BLOCK), BP_BLOCK, smem, (cudaStream_t)stream>>>(*w, *o, make_pb(params), iter)));
     }
     return check(cudaGetLastError(), "k_backpass");
 }
@@ -118,7 +126,7 @@ int ilqgk_launch_ls_reset(const ilqg_work *w, void *stream)
 
 int ilqgk_launch_ls_round(const ilqg_work *w, const ilqg_opts *o, const double *params, int iter, int round, void *stream)
 {
-    k_ls_round<P><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, make_pb(params), iter, round);
+    PP_DISPATCH(w, (k_ls_round<P, PP><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, make_pb(params), iter, round)));
     return check(cudaGetLastError(), "k_ls_round");
 }
 
@@ -126,16 +134,16 @@ int ilqgk_launch_ls_tail(const ilqg_work *w, const ilqg_opts *o, const double *p
 {
     const int nrem = o->n_alpha - from;
     const ParamBlock<P> pb = make_pb(params);
-    k_ls_tail<P><<<nblk(w->B * nrem, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, pb, from);
+    PP_DISPATCH(w, (k_ls_tail<P, PP><<<nblk(w->B * nrem, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, pb, from)));
     if (check(cudaGetLastError(), "k_ls_tail")) return -1;
-    k_ls_commit<P><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, pb, iter, from);
+    PP_DISPATCH(w, (k_ls_commit<P, PP><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, pb, iter, from)));
     return check(cudaGetLastError(), "k_ls_commit");
 }
 
 int ilqgk_launch_post(const ilqg_work *w, const ilqg_opts *o, const double *params, void *stream)
 {
     if (P::N_MU_R + P::N_MU_F == 0) return 0;   /* cost does not depend on multipliers/penalties: nothing to redo */
-    k_post<P><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, make_pb(params));
+    PP_DISPATCH(w, (k_post<P, PP><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, make_pb(params))));
     return check(cudaGetLastError(), "k_post");
 }
 

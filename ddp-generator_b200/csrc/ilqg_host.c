@@ -31,6 +31,7 @@ struct chunk {
     double *params;        /* flat, time-invariant */
     double *d_kp[16];      /* [k]-indexed parameters: device arrays of n_hor + 1 doubles, in parameter order */
     double **d_pk;         /* device table of those pointers (ilqg_work.pk) */
+    double *d_pp;          /* per-problem parameter sets [npf][Bp] (ilqg_work.pp), allocated on first use */
     void *stream;
     int owns_stream;
     int iter;              /* pass index of the running problems */
@@ -205,6 +206,57 @@ static const char *ck_set_opt(chunk *h, const char *name, const double *value, i
     return NULL; /* debug_level */
 }
 
+static int param_offset(int index)
+{
+    int i, off = 0;
+    for (i = 0; i < index; i++)
+        if (ilqgk_param_size(i) > 0) off += ilqgk_param_size(i);
+    return off;
+}
+
+/* one row [Bp] of the per-problem table = the same value for every problem */
+static int pp_fill_row(chunk *h, int row, double v)
+{
+    size_t b;
+    double *tmp = (double *)malloc(sizeof(double) * h->Bp);
+    int rc;
+    for (b = 0; b < (size_t)h->Bp; b++) tmp[b] = v;
+    rc = ilqgk_h2d(h->d_pp + (size_t)row * h->Bp, tmp, sizeof(double) * h->Bp, h->stream) || ilqgk_stream_sync(h->stream);
+    free(tmp);
+    return rc ? failk(h) : 0;
+}
+
+/* parameter `index` for every problem of the chunk: value[b][n] (a batch of independent reference calls, each with
+   its own parameter struct).  The first call switches the chunk to per-problem parameters, seeded from the shared set. */
+static int ck_set_param_batch(chunk *h, int index, const double *value, int n)
+{
+    int i, off;
+    size_t b;
+    double *tmp;
+    if (index < 0 || index >= ilqgk_param_count()) return fail(h, "parameter index out of range");
+    if (ilqgk_param_size(index) == -1) return fail(h, "[k]-indexed parameters are shared by the batch");
+    if (n != ilqgk_param_size(index)) return fail(h, "wrong parameter length");
+    if (ilqgk_set_device(h->device)) return failk(h);
+    if (!h->d_pp) {
+        h->d_pp = (double *)dalloc(h, sizeof(double) * (size_t)(h->d.npf > 0 ? h->d.npf : 1) * h->Bp);
+        if (!h->d_pp) return -1;
+        for (i = 0; i < h->d.npf; i++)
+            if (pp_fill_row(h, i, h->params[i])) return -1;
+        h->w.pp = h->d_pp;
+    }
+    off = param_offset(index);
+    tmp = (double *)calloc((size_t)h->Bp, sizeof(double));
+    for (i = 0; i < n; i++) {
+        for (b = 0; b < (size_t)h->B; b++) tmp[b] = value[b * n + i];
+        if (ilqgk_h2d(h->d_pp + (size_t)(off + i) * h->Bp, tmp, sizeof(double) * h->Bp, h->stream) || ilqgk_stream_sync(h->stream)) {
+            free(tmp);
+            return failk(h);
+        }
+    }
+    free(tmp);
+    return 0;
+}
+
 static int ck_set_param(chunk *h, int index, const double *value, int n)
 {
     int i, off = 0;
@@ -222,6 +274,9 @@ static int ck_set_param(chunk *h, int index, const double *value, int n)
     for (i = 0; i < index; i++)
         if (ilqgk_param_size(i) > 0) off += ilqgk_param_size(i);
     memcpy(h->params + off, value, sizeof(double) * n);
+    if (h->d_pp) /* per-problem table in use: a shared value overwrites every problem's entry */
+        for (i = 0; i < n; i++)
+            if (pp_fill_row(h, off + i, value[i])) return -1;
     return 0;
 }
 
@@ -879,6 +934,14 @@ int ilqgb_set_param(ilqgb_handle *h, int index, const double *value, int n)
     int i;
     for (i = 0; i < h->n; i++)
         if (ck_set_param(h->c[i], index, value, n)) return hfail(h, h->c[i]);
+    return 0;
+}
+
+int ilqgb_set_param_batch(ilqgb_handle *h, int index, const double *value, int n)
+{
+    int i;
+    for (i = 0; i < h->n; i++)
+        if (ck_set_param_batch(h->c[i], index, value + (size_t)h->first[i] * n, n)) return hfail(h, h->c[i]);
     return 0;
 }
 

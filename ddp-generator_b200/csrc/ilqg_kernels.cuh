@@ -47,6 +47,17 @@ using Work = ilqg_work;
 
 template <class P> struct ParamBlock { double v[P::NPF]; };
 
+/* Problem parameters: shared by the batch (kernel-argument block, constant bank) or, when PP, one set per problem read
+   from w.pp ([NPF][Bp], problem index fastest) into the thread's registers -- a batch of independent reference calls,
+   each with its own parameter struct (iLQG_mex.c:70-84). */
+#define ILQG_PARAMS(PP_, b_)                                                                   \
+    double pl_[(PP_) ? P::NPF : 1];                                                            \
+    const double *pv = pb.v;                                                                   \
+    if (PP_) {                                                                                 \
+        _Pragma("unroll") for (int i_ = 0; i_ < P::NPF_USED; i_++) pl_[i_] = w.pp[(size_t)i_ * w.Bp + (b_)]; \
+        pv = pl_;                                                                              \
+    }
+
 #ifndef ILQG_FORCE_COOP
 #define ILQG_FORCE_COOP 0
 #endif
@@ -389,13 +400,14 @@ __device__ __forceinline__ void lower_lambda(const Opts &o, double &lambda, doub
 /* =====================================================================================================================
  * K1: derivative pass, one thread per (problem, timestep); k == T evaluates the final-cost derivatives.
  * ===================================================================================================================== */
-template <class P, bool FULL>
+template <class P, bool FULL, bool PP>
 __global__ void __launch_bounds__(DV_BLOCK) k_derivs(Work w, ParamBlock<P> pb)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y;
     if (b >= w.B) return;
     if (w.status[b] != ST_RUNNING || !w.new_deriv[b]) return;
+    ILQG_PARAMS(PP, b)
     const size_t Bp = w.Bp;
     const int cur = w.cur[b];
     constexpr int RXU = Rec<P>::RXU;
@@ -409,9 +421,9 @@ __global__ void __launch_bounds__(DV_BLOCK) k_derivs(Work w, ParamBlock<P> pb)
         double v1[P::NV1], v2[P::NV2];
         const double w_pen = w.w_pen_l[b];
         if (FULL)
-            ok = P::derivs_full(x, u, pb.v, w.pk, k, w.T, w_pen, mu, v1, v2);
+            ok = P::derivs_full(x, u, pv, w.pk, k, w.T, w_pen, mu, v1, v2);
         else
-            ok = P::derivs(x, u, pb.v, w.pk, k, w.T, w_pen, mu, v1, v2);
+            ok = P::derivs(x, u, pv, w.pk, k, w.T, w_pen, mu, v1, v2);
         if (use_coop<P>()) { /* one contiguous record per (step, problem): the consumer is a whole warp per problem */
             double *o1 = w.V1 + ((size_t)k * Bp + b) * P::NV1;
 #pragma unroll
@@ -435,7 +447,7 @@ __global__ void __launch_bounds__(DV_BLOCK) k_derivs(Work w, ParamBlock<P> pb)
 #pragma unroll
         for (int i = 0; i < P::N_MU_F; i++) mu[i] = w.muF[(size_t)i * Bp + b];
         double cx[P::NX], cxx[P::NQXX];
-        ok = P::derivs_final(x, pb.v, w.pk, w.T, w.T, w.w_pen_f[b], mu, cx, cxx);
+        ok = P::derivs_final(x, pv, w.pk, w.T, w.T, w.w_pen_f[b], mu, cx, cxx);
         double *fd = w.FD + b;
 #pragma unroll
         for (int i = 0; i < P::NX; i++) fd[i * Bp] = cx[i];
@@ -474,7 +486,7 @@ __device__ __forceinline__ void bp_issue(const Work &w, double *sm, int k, int s
 
 /* MINB = minimum resident blocks per SM the compiler must allow: 8 caps the kernel at 128 registers (16 warps/SM, the
    throughput build for large batches); 1 leaves registers free (no spills, shortest per-step latency, small batches) */
-template <class P, bool FULL, int MINB>
+template <class P, bool FULL, int MINB, bool PP>
 __global__ void __launch_bounds__(BP_BLOCK, MINB) k_backpass(Work w, Opts o, ParamBlock<P> pb, int iter)
 {
     constexpr int NX = P::NX, NU = P::NU, NQXX = P::NQXX, NQUU = P::NQUU, NQXU = P::NQXU;
@@ -483,6 +495,7 @@ __global__ void __launch_bounds__(BP_BLOCK, MINB) k_backpass(Work w, Opts o, Par
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= w.B) return;
     if (w.status[b] != ST_RUNNING) return;
+    ILQG_PARAMS(PP, b)
     if (w.new_deriv[b]) {
         if (w.deriv_fail[b]) { /* "Calculating derivatives failed": break (iLQG.c:248-251) */
             finish(w, b, iter, w.bp_done[b] ? 1 : 0);
@@ -496,7 +509,7 @@ __global__ void __launch_bounds__(BP_BLOCK, MINB) k_backpass(Work w, Opts o, Par
     const int cur = w.cur[b];
     double lambda = w.lambda[b], dlambda = w.dlambda[b];
     Dense<P> D;
-    P::consts(pb.v, D);
+    P::consts(pv, D);
 
     double Vx[NX], Vxx[NQXX];
     double dV0 = 0.0, dV1 = 0.0, g_sum = 0.0;
@@ -553,9 +566,9 @@ __global__ void __launch_bounds__(BP_BLOCK, MINB) k_backpass(Work w, Opts o, Par
                 double v2[P::NV2];
 #pragma unroll
                 for (int i = 0; i < P::NV2_USED; i++) v2[i] = st[(P::NV1 + NU + i) * BP_BLOCK];
-                P::add2_Qxu(Vx, v2, pb.v, Qxu);
-                P::add2_Quu(Vx, v2, pb.v, Quu);
-                P::add2_Qxx(Vx, v2, pb.v, Qxx);
+                P::add2_Qxu(Vx, v2, pv, Qxu);
+                P::add2_Quu(Vx, v2, pv, Quu);
+                P::add2_Qxx(Vx, v2, pv, Qxx);
             }
             /* regularisation (back_pass.c:134-159) */
 #pragma unroll
@@ -752,7 +765,7 @@ __device__ __forceinline__ void tri_rc(int e, int &r, int &c)
     r = e - (c * (c + 1)) / 2;
 }
 
-template <class P, bool FULL>
+template <class P, bool FULL, bool PP>
 __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_warp(Work w, Opts o, ParamBlock<P> pb, int iter)
 {
     constexpr int NX = P::NX, NU = P::NU, NQXX = P::NQXX, NQUU = P::NQUU, NQXU = P::NQXU;
@@ -763,6 +776,7 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
     const int b = blockIdx.x * CW_WARPS + wid;
     if (b >= w.B) return;
     if (w.status[b] != ST_RUNNING) return;
+    ILQG_PARAMS(PP, b)
     CoopWS<P> &ws = ws_all[wid];
     if (w.new_deriv[b]) {
         if (w.deriv_fail[b]) {
@@ -781,8 +795,8 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
     double lambda = w.lambda[b], dlambda = w.dlambda[b];
     double *Dd = reinterpret_cast<double *>(&ws.D);
     if (lane == 0) {
-        P::consts(pb.v, ws.D);
-        if (FULL) P::consts2(pb.v, ws.c2);
+        P::consts(pv, ws.D);
+        if (FULL) P::consts2(pv, ws.c2);
     }
     for (int e = lane; e < NQXX; e += 32) {
         int r, c;
@@ -1155,7 +1169,7 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
  * iLQG.c:306-361).
  * ===================================================================================================================== */
 template <class P, bool STORE = true>
-__device__ __forceinline__ bool rollout(const Work &w, const ParamBlock<P> &pb, int b, int from, int to, double alpha,
+__device__ __forceinline__ bool rollout(const Work &w, const double *pv, int b, int from, int to, double alpha,
                                         double w_pen_l, double w_pen_f, double &csum)
 {
     constexpr int NX = P::NX, NU = P::NU, RXU = Rec<P>::RXU, RLL = Rec<P>::RLL;
@@ -1202,7 +1216,7 @@ __device__ __forceinline__ bool rollout(const Work &w, const ParamBlock<P> &pb, 
 #pragma unroll
         for (int i = 0; i < P::N_MU_R; i++) mu[i] = w.muR[((size_t)k * P::N_MU_R + i) * Bp + b];
         double c;
-        const bool ok = P::step(x, u, pb.v, w.pk, k, T, w_pen_l, mu, xn, c);
+        const bool ok = P::step(x, u, pv, w.pk, k, T, w_pen_l, mu, xn, c);
         if (STORE) st_rec<RXU>(w.XU[to] + ((size_t)k * Bp + b) * RXU, xu);
         if (!ok) return false;
         csum += c;
@@ -1221,14 +1235,14 @@ __device__ __forceinline__ bool rollout(const Work &w, const ParamBlock<P> &pb, 
 #pragma unroll
     for (int i = 0; i < P::N_MU_F; i++) mu[i] = w.muF[(size_t)i * Bp + b];
     double c;
-    if (!P::final_cost(x, pb.v, w.pk, T, T, w_pen_f, mu, c)) return false;
+    if (!P::final_cost(x, pv, w.pk, T, T, w_pen_f, mu, c)) return false;
     csum += c;
     return true;
 }
 
 /* cost-only pass over the nominal trajectory (forward_pass with cost_only = 1) */
 template <class P>
-__device__ __forceinline__ bool cost_pass(const Work &w, const ParamBlock<P> &pb, int b, int buf, double w_pen_l,
+__device__ __forceinline__ bool cost_pass(const Work &w, const double *pv, int b, int buf, double w_pen_l,
                                           double w_pen_f, double &csum)
 {
     constexpr int NX = P::NX, NU = P::NU, RXU = Rec<P>::RXU;
@@ -1241,25 +1255,26 @@ __device__ __forceinline__ bool cost_pass(const Work &w, const ParamBlock<P> &pb
 #pragma unroll
         for (int i = 0; i < P::N_MU_R; i++) mu[i] = w.muR[((size_t)k * P::N_MU_R + i) * Bp + b];
         double c;
-        if (!P::step_cost(xu, xu + NX, pb.v, w.pk, k, T, w_pen_l, mu, c)) return false;
+        if (!P::step_cost(xu, xu + NX, pv, w.pk, k, T, w_pen_l, mu, c)) return false;
         csum += c;
     }
     ld_rec<NX>(w.XU[buf] + ((size_t)T * Bp + b) * RXU, xu);
 #pragma unroll
     for (int i = 0; i < P::N_MU_F; i++) mu[i] = w.muF[(size_t)i * Bp + b];
     double c;
-    if (!P::final_cost(xu, pb.v, w.pk, T, T, w_pen_f, mu, c)) return false;
+    if (!P::final_cost(xu, pv, w.pk, T, T, w_pen_f, mu, c)) return false;
     csum += c;
     return true;
 }
 
 enum { INIT_MULT = 1, INIT_ROLLOUT = 2, INIT_BEGIN = 4, INIT_ALL = 7 };
 
-template <class P>
+template <class P, bool PP>
 __global__ void __launch_bounds__(BP_BLOCK) k_init(Work w, Opts o, ParamBlock<P> pb, int mode)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= w.B) return;
+    ILQG_PARAMS(PP, b)
     const size_t Bp = w.Bp;
     const int T = w.T;
     if (mode & INIT_MULT) { /* init_multipliers (iLQG_func.tem:364-400) */
@@ -1281,7 +1296,7 @@ __global__ void __launch_bounds__(BP_BLOCK) k_init(Work w, Opts o, ParamBlock<P>
     bool ok = true;
     if (mode & INIT_ROLLOUT) {
         double csum;
-        ok = rollout<P>(w, pb, b, 0, 1, 0.0, 0.0, 0.0, csum);
+        ok = rollout<P>(w, pv, b, 0, 1, 0.0, 0.0, 0.0, csum);
         w.cur[b] = 1;
         w.cost[b] = csum;
         w.new_cost[b] = csum;
@@ -1324,7 +1339,7 @@ __global__ void __launch_bounds__(BP_BLOCK) k_init(Work w, Opts o, ParamBlock<P>
             for (int i = 0; i < P::NU; i++) u[i] = xu[P::NX + i];
 #pragma unroll
             for (int i = 0; i < P::N_MU_R; i++) mu[i] = w.muR[(size_t)i * Bp + b];
-            P::mult_running(x, u, pb.v, w.pk, 0, T, o.w_pen_init_l, mu, hval, mun);
+            P::mult_running(x, u, pv, w.pk, 0, T, o.w_pen_init_l, mu, hval, mun);
 #pragma unroll
             for (int i = 0; i < P::N_MU_R; i++) w.lastR[(size_t)i * Bp + b] = hval[i];
         }
@@ -1332,7 +1347,7 @@ __global__ void __launch_bounds__(BP_BLOCK) k_init(Work w, Opts o, ParamBlock<P>
             ld_rec<P::NX>(w.XU[nb] + ((size_t)T * Bp + b) * Rec<P>::RXU, x);
 #pragma unroll
             for (int i = 0; i < P::N_MU_F; i++) mu[i] = w.muF[(size_t)i * Bp + b];
-            P::mult_final(x, pb.v, w.pk, T, T, o.w_pen_init_f, mu, hval, mun);
+            P::mult_final(x, pv, w.pk, T, T, o.w_pen_init_f, mu, hval, mun);
 #pragma unroll
             for (int i = 0; i < P::N_MU_F; i++) w.lastF[(size_t)i * Bp + b] = hval[i];
         }
@@ -1342,15 +1357,16 @@ __global__ void __launch_bounds__(BP_BLOCK) k_init(Work w, Opts o, ParamBlock<P>
 /* forward_pass(candidate, o, alpha, &csum, cost_only) of the single-problem API on its own (iLQG_func.tem:121-185):
  * one rollout from the nominal buffer into the other one (or the cost-only pass over the nominal); csum -> new_cost,
  * success flag -> result.  No solver bookkeeping. */
-template <class P>
+template <class P, bool PP>
 __global__ void __launch_bounds__(BP_BLOCK) k_rollout_only(Work w, ParamBlock<P> pb, double alpha, int cost_only)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= w.B) return;
+    ILQG_PARAMS(PP, b)
     const int cur = w.cur[b];
     double csum;
-    const bool ok = cost_only ? cost_pass<P>(w, pb, b, cur, w.w_pen_l[b], w.w_pen_f[b], csum)
-                              : rollout<P>(w, pb, b, cur, cur ^ 1, alpha, w.w_pen_l[b], w.w_pen_f[b], csum);
+    const bool ok = cost_only ? cost_pass<P>(w, pv, b, cur, w.w_pen_l[b], w.w_pen_f[b], csum)
+                              : rollout<P>(w, pv, b, cur, cur ^ 1, alpha, w.w_pen_l[b], w.w_pen_f[b], csum);
     w.new_cost[b] = csum;
     w.result[b] = ok ? 1 : 0;
 }
@@ -1395,7 +1411,7 @@ __device__ __forceinline__ void ls_decide(const Work &w, const Opts &o, int b, i
  * while one neighbour backtracks.  The list keeps the problems of a block in order, which keeps most 32-byte
  * sectors shared between neighbouring lanes.  The problem that accepts, or exhausts the alphas, runs the
  * accept/reject bookkeeping of iLQG.c:311-361 in the same thread. */
-template <class P>
+template <class P, bool PP>
 __global__ void __launch_bounds__(BP_BLOCK, ILQG_LS_MINBLOCKS)
 k_ls_round(Work w, Opts o, ParamBlock<P> pb, int iter, int round)
 {
@@ -1409,6 +1425,7 @@ k_ls_round(Work w, Opts o, ParamBlock<P> pb, int iter, int round)
     }
     bool undecided = false;
     if (b >= 0) {
+        ILQG_PARAMS(PP, b)
         const int cur = w.cur[b];
         const double cost = w.cost[b], dV0 = w.dV0[b], dV1 = w.dV1[b];
         double w_pen_l = w.w_pen_l[b], w_pen_f = w.w_pen_f[b];
@@ -1420,7 +1437,7 @@ k_ls_round(Work w, Opts o, ParamBlock<P> pb, int iter, int round)
         w.n_roll[b] += 1;
         const double alpha = o.alpha[round];
         bool accepted = false;
-        const bool ok = rollout<P>(w, pb, b, cur, cur ^ 1, alpha, w_pen_l, w_pen_f, cnew);
+        const bool ok = rollout<P>(w, pv, b, cur, cur ^ 1, alpha, w_pen_l, w_pen_f, cnew);
         if (ok) {
             dcost = cost - cnew;
             expected = -alpha * (dV0 + alpha * dV1);
@@ -1466,7 +1483,7 @@ k_ls_round(Work w, Opts o, ParamBlock<P> pb, int iter, int round)
  * (problem, alpha), without storing trajectories; k_ls_commit then replays the reference's sequential decision over
  * the recorded costs (first alpha with z > zMin wins, line_search.c:37-60) and re-runs only the winning rollout with
  * stores.  The line search then costs from + 2 rollout latencies instead of n_alpha; results are bit-identical. */
-template <class P>
+template <class P, bool PP>
 __global__ void __launch_bounds__(BP_BLOCK, ILQG_LS_MINBLOCKS) k_ls_tail(Work w, Opts o, ParamBlock<P> pb, int from)
 {
     const int nrem = o.n_alpha - from;
@@ -1474,10 +1491,11 @@ __global__ void __launch_bounds__(BP_BLOCK, ILQG_LS_MINBLOCKS) k_ls_tail(Work w,
     const int i = tid / nrem, a = from + tid % nrem;
     if (i >= w.ls_count[from]) return;
     const int b = w.ls_list[from & 1][i];
+    ILQG_PARAMS(PP, b)
     const int cur = w.cur[b];
     const double alpha = o.alpha[a];
     double cnew;
-    const bool ok = rollout<P, false>(w, pb, b, cur, cur ^ 1, alpha, w.w_pen_l[b], w.w_pen_f[b], cnew);
+    const bool ok = rollout<P, false>(w, pv, b, cur, cur ^ 1, alpha, w.w_pen_l[b], w.w_pen_f[b], cnew);
     w.ls_cnew[(size_t)a * w.Bp + b] = cnew;
     if (ok) {
         const double dcost = w.cost[b] - cnew;
@@ -1487,12 +1505,13 @@ __global__ void __launch_bounds__(BP_BLOCK, ILQG_LS_MINBLOCKS) k_ls_tail(Work w,
     }
 }
 
-template <class P>
+template <class P, bool PP>
 __global__ void __launch_bounds__(BP_BLOCK, ILQG_LS_MINBLOCKS) k_ls_commit(Work w, Opts o, ParamBlock<P> pb, int iter, int from)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= w.ls_count[from]) return;
     const int b = w.ls_list[from & 1][tid];
+    ILQG_PARAMS(PP, b)
     const size_t Bp = w.Bp;
     const int cur = w.cur[b];
     const int mask = w.ls_mask[b];
@@ -1517,7 +1536,7 @@ __global__ void __launch_bounds__(BP_BLOCK, ILQG_LS_MINBLOCKS) k_ls_commit(Work 
     w.n_roll[b] += (win >= 0 ? 1 : 0);
     if (win >= 0) {
         double c2;
-        rollout<P, true>(w, pb, b, cur, cur ^ 1, o.alpha[win], w_pen_l, w_pen_f, c2); /* same arithmetic -> same cost */
+        rollout<P, true>(w, pv, b, cur, cur ^ 1, o.alpha[win], w_pen_l, w_pen_f, c2); /* same arithmetic -> same cost */
         cnew = c2;
     }
     w.new_cost[b] = cnew;
@@ -1528,7 +1547,7 @@ __global__ void __launch_bounds__(BP_BLOCK, ILQG_LS_MINBLOCKS) k_ls_commit(Work 
 
 /* K5: update_multipliers(o, 0) and the cost-only pass that follows an accepted step, or the cost-only pass after a
  * rejected step whose penalty weights grew (iLQG.c:337-338, 345-349).  Only launched for problems with multipliers. */
-template <class P>
+template <class P, bool PP>
 __global__ void __launch_bounds__(BP_BLOCK) k_post(Work w, Opts o, ParamBlock<P> pb)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1536,6 +1555,7 @@ __global__ void __launch_bounds__(BP_BLOCK) k_post(Work w, Opts o, ParamBlock<P>
     const int mode = w.post_mode[b];
     if (mode == POST_NONE) return;
     w.post_mode[b] = POST_NONE;
+    ILQG_PARAMS(PP, b)
     constexpr int NX = P::NX, NU = P::NU, NR = P::N_MU_R, NF = P::N_MU_F;
     const size_t Bp = w.Bp;
     const int T = w.T;
@@ -1554,7 +1574,7 @@ __global__ void __launch_bounds__(BP_BLOCK) k_post(Work w, Opts o, ParamBlock<P>
                 for (int j = 0; j < NU; j++) u[j] = xu[NX + j];
 #pragma unroll
                 for (int i = 0; i < NR; i++) mu[i] = w.muR[((size_t)k * NR + i) * Bp + b];
-                P::mult_running(x, u, pb.v, w.pk, k, T, w_pen_l, mu, hval, mun);
+                P::mult_running(x, u, pv, w.pk, k, T, w_pen_l, mu, hval, mun);
 #pragma unroll
                 for (int i = 0; i < NR; i++) {
                     double *last = &w.lastR[((size_t)k * NR + i) * Bp + b];
@@ -1574,7 +1594,7 @@ __global__ void __launch_bounds__(BP_BLOCK) k_post(Work w, Opts o, ParamBlock<P>
             ld_rec<NX>(w.XU[cur] + ((size_t)T * Bp + b) * Rec<P>::RXU, x);
 #pragma unroll
             for (int i = 0; i < NF; i++) mu[i] = w.muF[(size_t)i * Bp + b];
-            P::mult_final(x, pb.v, w.pk, T, T, w_pen_f, mu, hval, mun);
+            P::mult_final(x, pv, w.pk, T, T, w_pen_f, mu, hval, mun);
 #pragma unroll
             for (int i = 0; i < NF; i++) {
                 double *last = &w.lastF[(size_t)i * Bp + b];
@@ -1592,7 +1612,7 @@ __global__ void __launch_bounds__(BP_BLOCK) k_post(Work w, Opts o, ParamBlock<P>
         w.w_pen_f[b] = w_pen_f;
     }
     double csum;
-    cost_pass<P>(w, pb, b, cur, w_pen_l, w_pen_f, csum);
+    cost_pass<P>(w, pv, b, cur, w_pen_l, w_pen_f, csum);
     w.cost[b] = csum;
 }
 

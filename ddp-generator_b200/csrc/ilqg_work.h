@@ -28,6 +28,7 @@ typedef struct ilqg_work {
     double *V1, *V2, *FD;      /* time-varying derivative entries [T][NV1][Bp], [T][NV2][Bp]; final cx,cxx [NX+NQXX][Bp] */
     double *muR, *lastR, *muF, *lastF;
     const double *const *pk;   /* [k]-indexed parameters (device pointers), or null */
+    const double *pp;          /* per-problem parameter sets [NPF][Bp], or null = one shared set (kernel argument) */
     double *cost, *new_cost, *dcost, *expected, *lambda, *dlambda, *g_norm, *dV0, *dV1, *w_pen_l, *w_pen_f;
     int *cur, *status, *new_deriv, *deriv_fail, *iterations, *result, *n_ls, *n_bp, *bp_done, *post_mode;
     int *ls_list[2], *ls_count; /* line search: compacted lists of undecided problems (ping-pong), per-round counts */

@@ -65,6 +65,7 @@ class Library:
         L.ilqgb_set_opt.restype = cp
         L.ilqgb_set_opt.argtypes = [vp, cp, dp, ci]
         L.ilqgb_set_param.argtypes = [vp, ci, dp, ci]
+        L.ilqgb_set_param_batch.argtypes = [vp, ci, dp, ci]
         L.ilqgb_validate_opt.restype = cp
         L.ilqgb_validate_opt.argtypes = [cp, dp, ci]
         L.ilqgb_upload.argtypes = [vp, dp, dp]
@@ -143,6 +144,13 @@ class BatchSolver:
                 raise KeyError(f"Parameter name '{name}' is not member of parameters struct.")
             v = np.ascontiguousarray(np.asarray(params[name], dtype=np.float64).ravel())
             self._chk(self.lib.ilqgb_set_param(self.h, i, _ptr(v), v.size))
+
+    def set_params_batch(self, params):
+        """Per-problem parameter sets: {name: array [batch, size]} for the names that differ between problems."""
+        for name, val in params.items():
+            i = self.L.param_names.index(name)
+            v = np.ascontiguousarray(np.asarray(val, dtype=np.float64).reshape(self.B, -1))
+            self._chk(self.lib.ilqgb_set_param_batch(self.h, i, _ptr(v), v.shape[1]))
 
     # data ----------------------------------------------------------------------------------------------------------------
     def upload(self, x0, u0):

@@ -59,6 +59,9 @@ void ilqgb_standard_parameters(ilqgb_handle *h);
 const char *ilqgb_set_opt(ilqgb_handle *h, const char *name, const double *value, int n); /* NULL = ok */
 const char *ilqgb_validate_opt(const char *name, const double *value, int n);               /* same check, no handle */
 int ilqgb_set_param(ilqgb_handle *h, int index, const double *value, int n);
+/* one value set per problem: value[batch][n].  A batch is then B independent reference calls, each with its own parameter
+ * struct (iLQG_mex.c:70-84); parameters never set this way keep the shared value.  Not for [k]-indexed parameters. */
+int ilqgb_set_param_batch(ilqgb_handle *h, int index, const double *value, int n);
 
 /* host -> device: x0 [batch][nx], u_nom [batch][n_hor][nu] (problem-major, as a caller holds them) */
 int ilqgb_upload(ilqgb_handle *h, const double *x0, const double *u_nom);

@@ -172,3 +172,28 @@ def test_stepwise_iteration_and_caller_stream():
         s.close()
     for k in ("cost", "iterations", "n_linesearch", "success", "x", "u"):
         assert np.array_equal(got[k], want[k]), k
+
+
+def test_per_problem_parameter_sets():
+    """Every problem of a batch with its own parameter struct (limits, cost weights, geometry), like B independent calls
+    of the reference: bit-identical to solving each problem alone with its parameters."""
+    B, T = 37, 70
+    x0, u0 = W.car_batch(B, T=T, seed=81)
+    rng = np.random.default_rng(5)
+    limW = np.stack([-0.3 - 0.3 * rng.random(B), 0.3 + 0.3 * rng.random(B)], axis=1)
+    cf = np.array(W.CAR_PARAMS["cf"])[None, :] * (0.5 + rng.random((B, 4)))
+    d = 1.5 + rng.random((B, 1))
+    opts = {"max_iter": 8}
+    for chunks in (1, 2):
+        s = ilqg_b200.BatchSolver("car", 0, B, T, chunks=chunks)
+        s.set_options(opts); s.set_params(W.CAR_PARAMS)
+        s.set_params_batch({"limW": limW, "cf": cf, "d": d})
+        out = s.solve(x0, u0)
+        s.close()
+        O = _oracle("car", 0)
+        for b in range(B):
+            p = dict(W.CAR_PARAMS, limW=limW[b], cf=cf[b], d=d[b])
+            h = O.solver(T); h.set_opts(opts); h.set_params(p)
+            assert h.init(x0[b], u0[b]); h.solve()
+            assert out["cost"][b] == h.scalar("cost") and out["iterations"][b] == h.scalar("iterations"), (chunks, b)
+            assert np.array_equal(out["x"][b], h.get("x")) and np.array_equal(out["u"][b], h.get("u")), (chunks, b)
