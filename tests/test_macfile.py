@@ -56,8 +56,8 @@ def test_own_mac_file_generates_and_compiles():
                         os.path.join(d, "iLQG_func.c"), "-o", os.path.join(d, "f.o")], check=True)
         cu = os.path.join(d, "t.cu")
         open(cu, "w").write('#include "ilqg_kernels.cuh"\n#include "pendulum_device.cuh"\n'
-                            'template __global__ void ilqg::k_derivs<ProbPendulum, true>(ilqg_work, ilqg::ParamBlock<ProbPendulum>);\n'
-                            'template __global__ void ilqg::k_backpass<ProbPendulum, true, 8>(ilqg_work, ilqg_opts, ilqg::ParamBlock<ProbPendulum>, int);\n'
-                            'template __global__ void ilqg::k_ls_round<ProbPendulum>(ilqg_work, ilqg_opts, ilqg::ParamBlock<ProbPendulum>, int, int);\n')
+                            'template __global__ void ilqg::k_derivs<ProbPendulum, true, false>(ilqg_work, ilqg::ParamBlock<ProbPendulum>);\n'
+                            'template __global__ void ilqg::k_backpass<ProbPendulum, true, 8, true>(ilqg_work, ilqg_opts, ilqg::ParamBlock<ProbPendulum>, int);\n'
+                            'template __global__ void ilqg::k_ls_round<ProbPendulum, false>(ilqg_work, ilqg_opts, ilqg::ParamBlock<ProbPendulum>, int, int);\n')
         subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-fmad=false", "-diag-suppress", "550,177,20281",
                         *inc, "-c", cu, "-o", os.path.join(d, "t.o")], check=True)
