@@ -37,6 +37,7 @@ struct chunk {
     int iter;              /* pass index of the running problems */
     int ls_tail_from;      /* -1 = choose by batch size */
     int bp_latency;        /* -1 = choose by batch size */
+    int total_B;           /* problems of the whole handle (all chunks run concurrently on one GPU) */
     int started;
     int trace_cap;         /* max_iter the trace arrays were sized for */
     void **allocs;
@@ -306,6 +307,7 @@ static chunk *ck_create(int device, int batch, int n_hor, int flags, void *strea
     h = (chunk *)calloc(1, sizeof *h);
     h->device = device;
     h->B = batch;
+    h->total_B = batch;
     h->Bp = (batch + 31) / 32 * 32;
     h->T = n_hor;
     h->flags = flags;
@@ -580,7 +582,7 @@ static int launch_pass(chunk *h, int do_derivs, int do_back, int do_ls)
     }
     if (do_back) {
         p = timing_begin(h, TC_BACKPASS);
-        h->o.bp_latency_build = h->bp_latency >= 0 ? h->bp_latency : (h->B <= 40000);
+        h->o.bp_latency_build = h->bp_latency >= 0 ? h->bp_latency : (h->total_B <= 40000);
         if (ilqgk_launch_backpass(&h->w, &h->o, h->params, h->iter, h->stream)) return failk(h);
         h->n_launches++;
         timing_end(h, p);
@@ -591,7 +593,9 @@ static int launch_pass(chunk *h, int do_derivs, int do_back, int do_ls)
         {
             /* small batches: one sequential round, then all remaining alphas at once (latency-bound regime);
                large batches: one alpha per launch over the shrinking list of undecided problems (throughput-bound) */
-            int from = h->ls_tail_from >= 0 ? h->ls_tail_from : (h->B <= 40000 ? 1 : (h->B <= 100000 ? 3 : h->o.n_alpha));
+            /* thresholds measured on B200 (scripts/gpu_probe.py with ILQG_LS_TAIL_FROM), by problems resident on the GPU */
+            int from = h->ls_tail_from >= 0 ? h->ls_tail_from
+                                            : (h->total_B <= 20000 ? 1 : (h->total_B <= 50000 ? 2 : (h->total_B <= 140000 ? 3 : 4)));
             if (from < 1) from = 1;     /* round 0 builds the list of undecided problems the tail works on */
             if (from > h->o.n_alpha || h->o.n_alpha - from < 2) from = h->o.n_alpha;
             h->o.ls_tail_from = from;
@@ -896,6 +900,7 @@ ilqgb_handle *ilqgb_create(int device, int batch, int n_hor, int flags, void *st
         h->first[i] = first;
         h->c[i] = ck_create(device, cnt, n_hor, flags & 0xff, n == 1 ? h->stream : NULL);
         if (!h->c[i]) { ilqgb_destroy(h); return NULL; }
+        h->c[i]->total_B = batch;
     }
     if (h->n > 1) {
         if (ilqgk_event_create_notiming(&h->ev_fork)) { fail_create(ilqgk_last_error()); ilqgb_destroy(h); return NULL; }
