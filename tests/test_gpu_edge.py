@@ -197,3 +197,25 @@ def test_per_problem_parameter_sets():
             assert h.init(x0[b], u0[b]); h.solve()
             assert out["cost"][b] == h.scalar("cost") and out["iterations"][b] == h.scalar("iterations"), (chunks, b)
             assert np.array_equal(out["x"][b], h.get("x")) and np.array_equal(out["u"][b], h.get("u")), (chunks, b)
+
+
+@pytest.mark.parametrize("tail_from", ["1", "2", "8"])
+def test_non_finite_rollouts_inside_the_line_search(tail_from, monkeypatch):
+    """A regime where large-step rollouts leave the domain of the dynamics (sqrt of a negative number -> NaN guard ->
+    forward_pass returns 0, line_search.c:55-59) while smaller steps are fine; all three line-search schedules
+    (parallel tail after 1 or 2 rounds, purely sequential rounds) must replay the reference's decisions."""
+    monkeypatch.setenv("ILQG_LS_TAIL_FROM", tail_from)
+    B, T = 12, 80
+    x0, u0 = W.car_batch(B, T=T, seed=91)
+    x0[:, 3] = 1.5
+    u0 = u0 * 5
+    params = dict(W.CAR_PARAMS, d=[0.05], limA=[-20.0, 20.0])
+    opts = {"max_iter": 15}
+    recs = PU.gpu_records("car", 0, T, params, x0, u0, opts)
+    kind = PU.oracle_kinds("car", 0)[0]
+    deep = 0
+    for b in range(B):
+        ora = PU.oracle_record(kind, "car", 0, T, params, x0[b], u0[b], opts)
+        PU.assert_same(recs[b], ora, f"nan-regime b{b} tail_from={tail_from}")
+        deep += int((ora["tr_alpha"] >= 4).sum())
+    assert deep > 20      # the case really exercises deep backtracking
