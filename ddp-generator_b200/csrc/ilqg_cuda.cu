@@ -134,6 +134,7 @@ int ilqgk_launch_ls_tail(const ilqg_work *w, const ilqg_opts *o, const double *p
 {
     const int nrem = o->n_alpha - from;
     const ParamBlock<P> pb = make_pb(params);
+    if (from == 0 && check(cudaMemsetAsync(w->ls_mask, 0, sizeof(int) * w->Bp, (cudaStream_t)stream), "memset ls_mask")) return -1;
     PP_DISPATCH(w, (k_ls_tail<P, PP><<<nblk(w->B * nrem, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, pb, from)));
     if (check(cudaGetLastError(), "k_ls_tail")) return -1;
     PP_DISPATCH(w, (k_ls_commit<P, PP><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, pb, iter, from)));

@@ -595,8 +595,7 @@ static int launch_pass(chunk *h, int do_derivs, int do_back, int do_ls)
                large batches: one alpha per launch over the shrinking list of undecided problems (throughput-bound) */
             /* thresholds measured on B200 (scripts/gpu_probe.py with ILQG_LS_TAIL_FROM), by problems resident on the GPU */
             int from = h->ls_tail_from >= 0 ? h->ls_tail_from
-                                            : (h->total_B <= 20000 ? 1 : (h->total_B <= 50000 ? 2 : (h->total_B <= 140000 ? 3 : 4)));
-            if (from < 1) from = 1;     /* round 0 builds the list of undecided problems the tail works on */
+                                            : (h->total_B <= 17000 ? 0 : (h->total_B <= 24000 ? 1 : (h->total_B <= 50000 ? 2 : (h->total_B <= 140000 ? 3 : 4))));
             if (from > h->o.n_alpha || h->o.n_alpha - from < 2) from = h->o.n_alpha;
             h->o.ls_tail_from = from;
             for (r = 0; r < from; r++) {

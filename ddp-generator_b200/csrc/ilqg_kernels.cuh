@@ -1489,8 +1489,14 @@ __global__ void __launch_bounds__(BP_BLOCK, ILQG_LS_MINBLOCKS) k_ls_tail(Work w,
     const int nrem = o.n_alpha - from;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = tid / nrem, a = from + tid % nrem;
-    if (i >= w.ls_count[from]) return;
-    const int b = w.ls_list[from & 1][i];
+    int b;
+    if (from == 0) { /* no sequential round at all (very small batches): every running problem, every alpha */
+        if (i >= w.B || w.status[i] != ST_RUNNING) return;
+        b = i;
+    } else {
+        if (i >= w.ls_count[from]) return;
+        b = w.ls_list[from & 1][i];
+    }
     ILQG_PARAMS(PP, b)
     const int cur = w.cur[b];
     const double alpha = o.alpha[a];
@@ -1509,10 +1515,18 @@ template <class P, bool PP>
 __global__ void __launch_bounds__(BP_BLOCK, ILQG_LS_MINBLOCKS) k_ls_commit(Work w, Opts o, ParamBlock<P> pb, int iter, int from)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= w.ls_count[from]) return;
-    const int b = w.ls_list[from & 1][tid];
-    ILQG_PARAMS(PP, b)
     const size_t Bp = w.Bp;
+    int b;
+    if (from == 0) {
+        if (tid >= w.B || w.status[tid] != ST_RUNNING) return;
+        b = tid;
+        if (w.tr_lambda) w.tr_lambda[(size_t)iter * Bp + b] = w.lambda[b];
+        w.n_ls[b] += 1;
+    } else {
+        if (tid >= w.ls_count[from]) return;
+        b = w.ls_list[from & 1][tid];
+    }
+    ILQG_PARAMS(PP, b)
     const int cur = w.cur[b];
     const int mask = w.ls_mask[b];
     const double cost = w.cost[b], dV0 = w.dV0[b], dV1 = w.dV1[b];

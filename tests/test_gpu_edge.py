@@ -199,7 +199,7 @@ def test_per_problem_parameter_sets():
             assert np.array_equal(out["x"][b], h.get("x")) and np.array_equal(out["u"][b], h.get("u")), (chunks, b)
 
 
-@pytest.mark.parametrize("tail_from", ["1", "2", "8"])
+@pytest.mark.parametrize("tail_from", ["0", "1", "2", "8"])
 def test_non_finite_rollouts_inside_the_line_search(tail_from, monkeypatch):
     """A regime where large-step rollouts leave the domain of the dynamics (sqrt of a negative number -> NaN guard ->
     forward_pass returns 0, line_search.c:55-59) while smaller steps are fine; all three line-search schedules
