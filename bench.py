@@ -346,6 +346,18 @@ def main():
             kernels[k] = {"ms_total": ms, "launches": n, "ms_per_launch": ms / n, "algorithmic_bytes": alg[k],
                           "achieved_gbs": alg[k] / (ms * 1e-3) / 1e9 if ms > 0 else None,
                           "share_of_step": ms / max(sum(v[0] for v in ktime.values()), 1e-9)}
+    # backward pass: fp64-issue bound.  Algorithmic multiply+add count per (problem, step) from SURVEY.md 8d (dense formula,
+    # regType 1, no clamp) against the fp64 pipe peak measured on a B200 by csrc/fp64_peak.cu (profiles/fp64_peak_r01.json;
+    # no FMA contraction is allowed on this path, so the comparable peak is the DMUL+DADD instruction rate)
+    if "backpass" in kernels:
+        n_, m_ = nx, nu
+        pairs = 2 * n_**3 + 5 * n_**2 * m_ + 3 * n_ * m_**2 + n_**2 + 4 * n_ * m_ + 2 * m_**2 + m_
+        fp = os.path.join(ROOT, "profiles", "fp64_peak_r01.json")
+        peak64 = json.load(open(fp))["dmul_dadd_instr_per_s"] if os.path.exists(fp) else 1.847e13
+        dp = 2.0 * pairs * n_bp * T_HOR / (kernels["backpass"]["ms_total"] * 1e-3)
+        kernels["backpass"]["fp64"] = {"algorithmic_dp_instr_per_step": 2 * pairs, "achieved_dp_instr_per_s": dp,
+                                       "peak_dp_instr_per_s": peak64, "frac": dp / peak64,
+                                       "peak_source": "csrc/fp64_peak.cu on B200 (DMUL+DADD, no FMA)"}
     dom = max(kernels, key=lambda k: kernels[k]["ms_total"]) if kernels else None
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
