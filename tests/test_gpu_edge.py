@@ -219,3 +219,42 @@ def test_non_finite_rollouts_inside_the_line_search(tail_from, monkeypatch):
         PU.assert_same(recs[b], ora, f"nan-regime b{b} tail_from={tail_from}")
         deep += int((ora["tr_alpha"] >= 4).sum())
     assert deep > 20      # the case really exercises deep backtracking
+
+
+def test_config4_full_size_sample_parity():
+    """BASELINE config 4 at full size (262 144 car problems, T = 500; 4 concurrent chunks): problems next to every chunk
+    boundary and at both ends match the oracle bit for bit; a rerun is bit-identical."""
+    B, T, iters = 262144, 500, 4
+    x0 = np.empty((B, 4)); u0 = np.empty((B, T, 2))
+    for s0 in range(0, B, 32768):
+        a, b = W.car_batch(32768, T=T, first=s0)
+        x0[s0:s0 + 32768] = a; u0[s0:s0 + 32768] = b
+    s = ilqg_b200.BatchSolver("car", 0, B, T)
+    assert s.chunks() == 4
+    s.set_options({"max_iter": iters}); s.set_params(W.CAR_PARAMS)
+    out = s.solve(x0, u0, want_traj=False)
+    cost_again = s.solve(x0, u0, want_traj=False)["cost"]
+    assert np.array_equal(out["cost"], cost_again)
+    idx = np.concatenate([np.arange(0, 8), np.arange(65536 - 4, 65536 + 4), np.arange(131072 - 4, 131072 + 4),
+                          np.arange(196608 - 4, 196608 + 4), np.arange(B - 8, B)])
+    xs = s.get("x")[idx]
+    s.close()
+    ora = _oracle("car", 0).solve_batch(x0[idx], u0[idx], W.CAR_PARAMS, {"max_iter": float(iters)}, 4, want_traj=True)
+    assert np.array_equal(out["cost"][idx], ora["cost"]) and np.array_equal(out["iterations"][idx], ora["iterations"])
+    assert np.array_equal(out["n_linesearch"][idx], ora["n_linesearch"]) and np.array_equal(xs, ora["x"])
+    assert out["n_linesearch"].sum() == B * iters      # nobody converges within 4 passes on this workload
+
+
+def test_config5_full_size_sample_parity():
+    """BASELINE config 5 at full size (16 384 quadrotor problems, T = 1000, FULL_DDP = 1), a few passes."""
+    B, T, iters = 16384, 1000, 5
+    x0, u0 = W.quad_batch(B, T=T)
+    s = ilqg_b200.BatchSolver("quad", 1, B, T)
+    s.set_options({"max_iter": iters}); s.set_params(W.QUAD_PARAMS)
+    out = s.solve(x0, u0, want_traj=False)
+    idx = np.array([0, 1, 8191, 8192, B - 2, B - 1])
+    us = s.get("u")[idx]
+    s.close()
+    ora = _oracle("quad", 1).solve_batch(x0[idx], u0[idx], W.QUAD_PARAMS, {"max_iter": float(iters)}, 3, want_traj=True)
+    assert np.array_equal(out["cost"][idx], ora["cost"]) and np.array_equal(out["iterations"][idx], ora["iterations"])
+    assert np.array_equal(us, ora["u"])
