@@ -12,8 +12,8 @@ A "step" is one pass of the iLQG loop (derivative kernel, backward-pass kernel, 
 whole shard; K steps = a solve with max_iter = K.  W warm-up steps run first on the same inputs (a throw-away
 solve with max_iter = W).  `value` = (line searches performed by all problems on all ranks) / (max over ranks of
 the device time of the K timed steps incl. the initial rollout), inputs resident in HBM.  `e2e` = the same count
-over the time of upload (pinned host -> HBM) + solve + download of x, u, cost, iterations (HBM -> pinned host),
-through the public C ABI.  The iteration count follows SURVEY.md 8d: loop passes that reached line_search.
+over the time of ONE call of the public C ABI's end-to-end entry (ilqgb_solve_host): upload (pinned host -> HBM) + solve +
+download of x, u, cost, iterations (HBM -> pinned host), pipelined per chunk stream.  The iteration count follows SURVEY.md 8d: loop passes that reached line_search.
 
 `--impl reference` times the reference's own C solver (oracle/_ref, the unmodified sources compiled -O3
 -ffp-contract=off; falls back to the oracle port if that library is not present) on all host cores, one solver
@@ -298,9 +298,8 @@ def main():
     t0 = time.perf_counter()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
-    S.upload_ptr(x0_t.data_ptr(), u0_t.data_ptr())
-    S.run()
-    S.download_ptr(x_out.data_ptr(), u_out.data_ptr(), cost_out.data_ptr(), it_out.data_ptr(), res_out.data_ptr(), nls_out.data_ptr())
+    S.solve_host_ptr(x0_t.data_ptr(), u0_t.data_ptr(), x_out.data_ptr(), u_out.data_ptr(), cost_out.data_ptr(), it_out.data_ptr(),
+                     res_out.data_ptr(), nls_out.data_ptr())
     e3.record()
     torch.cuda.synchronize()
     wall_e2e = time.perf_counter() - t0

@@ -484,6 +484,31 @@ static int gather_to_host(chunk *h, const double *src, const double *alt, const 
     return 0;
 }
 
+/* download without intermediate synchronisation: x and u are staged in disjoint halves of the staging buffer */
+static int ck_download_async(chunk *h, double *x, double *u, double *cost, int *iterations, int *result, int *n_linesearch)
+{
+    const size_t B = (size_t)h->B, nxs = B * (h->T + 1) * h->d.nx, nus = B * h->T * h->d.nu;
+    if (ilqgk_set_device(h->device)) return failk(h);
+    if (ensure_stage(h, nxs + nus)) return -1;
+    if (x) {
+        const lay_t L = lay_rec(h, h->d.rxu, 0);
+        if (ilqgk_launch_gather(h->w.XU[0], h->w.XU[1], h->w.cur, h->d_stage, h->B, h->T + 1, h->d.nx, L.stride_k, L.stride_b, L.stride_i, L.off, h->stream)) return failk(h);
+        if (ilqgk_d2h(x, h->d_stage, sizeof(double) * nxs, h->stream)) return failk(h);
+        h->n_launches++;
+    }
+    if (u) {
+        const lay_t L = lay_rec(h, h->d.rxu, h->d.nx);
+        if (ilqgk_launch_gather(h->w.XU[0], h->w.XU[1], h->w.cur, h->d_stage + nxs, h->B, h->T, h->d.nu, L.stride_k, L.stride_b, L.stride_i, L.off, h->stream)) return failk(h);
+        if (ilqgk_d2h(u, h->d_stage + nxs, sizeof(double) * nus, h->stream)) return failk(h);
+        h->n_launches++;
+    }
+    if (cost && ilqgk_d2h(cost, h->w.cost, sizeof(double) * B, h->stream)) return failk(h);
+    if (iterations && ilqgk_d2h(iterations, h->w.iterations, sizeof(int) * B, h->stream)) return failk(h);
+    if (result && ilqgk_d2h(result, h->w.result, sizeof(int) * B, h->stream)) return failk(h);
+    if (n_linesearch && ilqgk_d2h(n_linesearch, h->w.n_ls, sizeof(int) * B, h->stream)) return failk(h);
+    return 0;
+}
+
 static int ck_download(chunk *h, double *x, double *u, double *cost, int *iterations, int *result, int *n_linesearch)
 {
     const size_t B = (size_t)h->B;
@@ -1036,6 +1061,41 @@ int ilqgb_solve(ilqgb_handle *h)
     for (i = 0; i < h->n; i++)   /* problems still running after the last pass hit the iteration limit */
         if (ilqgk_launch_finalize(&h->c[i]->w, h->c[i]->o.max_iter, h->c[i]->stream)) return hfail(h, NULL);
     return join_streams(h);
+}
+
+/* End to end from and to host buffers (pinned for full overlap): every chunk uploads, solves and downloads on its own
+   stream with no barrier in between, so the uploads of later chunks overlap the first passes of earlier ones and the
+   result copies of x and u are queued back to back.  (Descending stream priorities, to let early chunks finish and
+   download while later ones still compute, were measured and made things slightly slower; all chunks are equal.) */
+int ilqgb_solve_host(ilqgb_handle *h, const double *x0, const double *u_nom, double *x, double *u, double *cost,
+                     int *iterations, int *result, int *n_linesearch)
+{
+    int i, pass;
+    const int max_iter = h->c[0]->o.max_iter;
+    if (ilqgk_set_device(h->device)) return hfail(h, NULL);
+    if (fork_streams(h)) return -1;
+    for (i = 0; i < h->n; i++) {
+        chunk *c = h->c[i];
+        if (ck_upload(c, x0 + (size_t)h->first[i] * h->d.nx, u_nom + (size_t)h->first[i] * h->T * h->d.nu)) return hfail(h, c);
+        if (ck_start(c)) return hfail(h, c);
+    }
+    for (pass = 0; pass < max_iter; pass++) {
+        for (i = 0; i < h->n; i++) {
+            if (launch_pass(h->c[i], 1, 1, 1)) return hfail(h, h->c[i]);
+            h->c[i]->iter++;
+        }
+        if ((pass + 1) % (4 * ACTIVE_CHECK_EVERY) == 0 && pass + 1 < max_iter && ilqgb_active(h) == 0) break;
+    }
+    for (i = 0; i < h->n; i++) {
+        chunk *c = h->c[i];
+        const size_t f = (size_t)h->first[i];
+        if (ilqgk_launch_finalize(&c->w, c->o.max_iter, c->stream)) return hfail(h, NULL);
+        if (ck_download_async(c, x ? x + f * (h->T + 1) * h->d.nx : NULL, u ? u + f * h->T * h->d.nu : NULL, cost ? cost + f : NULL,
+                              iterations ? iterations + f : NULL, result ? result + f : NULL, n_linesearch ? n_linesearch + f : NULL))
+            return hfail(h, c);
+    }
+    if (join_streams(h)) return -1;
+    return ilqgb_sync(h);
 }
 
 int ilqgb_sync(ilqgb_handle *h)

@@ -74,6 +74,7 @@ class Library:
             getattr(L, f).argtypes = [vp]
         L.ilqgb_iterate.argtypes = [vp, ci]
         L.ilqgb_download.argtypes = [vp, dp, dp, dp, dp, dp, dp]
+        L.ilqgb_solve_host.argtypes = [vp, dp, dp, dp, dp, dp, dp, dp, dp]
         L.ilqgb_get.restype = C.c_long
         L.ilqgb_get.argtypes = [vp, cp, dp]
         L.ilqgb_get_int.restype = C.c_long
@@ -202,6 +203,18 @@ class BatchSolver:
         self.upload(x0, u0)
         self.run()
         return self.download(want_traj)
+
+    def solve_host_ptr(self, x0_ptr, u0_ptr, x_ptr, u_ptr, cost_ptr, it_ptr, res_ptr, nls_ptr):
+        """Pipelined upload + solve + download on raw host pointers (pinned memory for full overlap)."""
+        self._chk(self.lib.ilqgb_solve_host(self.h, *[C.c_void_p(p) if p else None for p in (x0_ptr, u0_ptr, x_ptr, u_ptr, cost_ptr, it_ptr, res_ptr, nls_ptr)]))
+
+    def solve_host(self, x0, u0):
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        u0 = np.ascontiguousarray(u0, dtype=np.float64)
+        x = np.empty((self.B, self.T + 1, self.nx)); u = np.empty((self.B, self.T, self.nu)); cost = np.empty(self.B)
+        it = np.empty(self.B, np.int32); res = np.empty(self.B, np.int32); nls = np.empty(self.B, np.int32)
+        self._chk(self.lib.ilqgb_solve_host(self.h, _ptr(x0), _ptr(u0), _ptr(x), _ptr(u), _ptr(cost), _ptr(it), _ptr(res), _ptr(nls)))
+        return dict(success=res, x=x, u=u, cost=cost, iterations=it, n_linesearch=nls)
 
     def phase(self, which):
         self._chk(getattr(self.lib, f"ilqgb_phase_{which}")(self.h))

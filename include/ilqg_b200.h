@@ -72,6 +72,10 @@ int ilqgb_iterate(ilqgb_handle *h, int n_passes); /* returns passes actually lau
 int ilqgb_finish(ilqgb_handle *h);
 int ilqgb_solve(ilqgb_handle *h);
 int ilqgb_sync(ilqgb_handle *h);
+/* upload + solve + download in one call, pipelined across the handle's chunks (host buffers should be pinned); same
+ * results as ilqgb_upload + ilqgb_solve + ilqgb_download.  Any output pointer may be NULL.  Synchronises. */
+int ilqgb_solve_host(ilqgb_handle *h, const double *x0, const double *u_nom, double *x, double *u, double *cost,
+                     int *iterations, int *result, int *n_linesearch);
 int ilqgb_active(ilqgb_handle *h); /* problems still running (synchronises) */
 
 /* device -> host; any pointer may be NULL. x [batch][n_hor+1][nx], u [batch][n_hor][nu] */

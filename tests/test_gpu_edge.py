@@ -172,6 +172,13 @@ def test_stepwise_iteration_and_caller_stream():
         s.close()
     for k in ("cost", "iterations", "n_linesearch", "success", "x", "u"):
         assert np.array_equal(got[k], want[k]), k
+    # the pipelined single-call path (upload + solve + download per chunk stream, descending stream priorities)
+    p = ilqg_b200.BatchSolver("car", 0, B, T, chunks=2)
+    p.set_options({"max_iter": 10}); p.set_params(W.CAR_PARAMS)
+    piped = p.solve_host(x0, u0)
+    p.close()
+    for k in ("cost", "iterations", "n_linesearch", "success", "x", "u"):
+        assert np.array_equal(piped[k], want[k]), k
 
 
 def test_per_problem_parameter_sets():
