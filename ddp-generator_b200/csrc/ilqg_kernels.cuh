@@ -400,15 +400,54 @@ __device__ __forceinline__ void lower_lambda(const Opts &o, double &lambda, doub
 /* =====================================================================================================================
  * K1: derivative pass, one thread per (problem, timestep); k == T evaluates the final-cost derivatives.
  * ===================================================================================================================== */
+/* rewrite one double in place: a store of exactly what is there, which the compiler must not drop */
+__device__ __forceinline__ void rewrite8(double *p)
+{
+    double v;
+    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    *p = v;
+}
+
 template <class P, bool FULL, bool PP>
 __global__ void __launch_bounds__(DV_BLOCK) k_derivs(Work w, ParamBlock<P> pb)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y;
-    if (b >= w.B) return;
-    if (w.status[b] != ST_RUNNING || !w.new_deriv[b]) return;
-    ILQG_PARAMS(PP, b)
+    /* fresh: this problem needs new derivatives (iLQG.c:240-253).  The entry-major stores below put four neighbouring problems
+       into one 32-byte sector, and a partially written sector costs a DRAM read-modify-write (measured with ncu once ~10 % of a
+       batch had finished: +2 GB DRAM reads per sweep and twice the kernel time).  So a sector is either skipped or written
+       whole: a lane that is not fresh but shares a sector with a fresh one re-evaluates its entries -- same nominal and
+       parameters, hence the same bits for a running problem; a finished problem's entries are never read again -- or, when the
+       derivatives depend on multipliers / penalty weights that may have moved since they were last evaluated (the reference
+       does not refresh them after a rejected step, iLQG.c:345-349), stores back what is there. */
+    constexpr bool KEEP = (P::N_MU_R + P::N_MU_F) > 0;
+    const bool inb = b < w.B;
+    const bool fresh = inb && w.status[b] == ST_RUNNING && w.new_deriv[b];
+    bool fill = false;
+    if (!use_coop<P>()) {
+        const unsigned m = __ballot_sync(0xffffffffu, fresh);
+        fill = inb && !fresh && ((m >> (threadIdx.x & 28)) & 0xfu) != 0u;
+    }
+    if (!fresh && !fill) return;
     const size_t Bp = w.Bp;
+    if (KEEP && fill) {
+        if (k < w.T) {
+            double *o1 = w.V1 + (size_t)k * P::NV1 * Bp + b;
+#pragma unroll
+            for (int i = 0; i < P::NV1; i++) rewrite8(o1 + i * Bp);
+            if (FULL) {
+                double *o2 = w.V2 + (size_t)k * P::NV2 * Bp + b;
+#pragma unroll
+                for (int i = 0; i < P::NV2_USED; i++) rewrite8(o2 + i * Bp);
+            }
+        } else {
+            double *fd = w.FD + b;
+#pragma unroll
+            for (int i = 0; i < P::NX + P::NQXX; i++) rewrite8(fd + i * Bp);
+        }
+        return;
+    }
+    ILQG_PARAMS(PP, b)
     const int cur = w.cur[b];
     constexpr int RXU = Rec<P>::RXU;
     double xu[RXU], mu[P::N_MU_R + P::N_MU_F + 1];
@@ -454,7 +493,7 @@ __global__ void __launch_bounds__(DV_BLOCK) k_derivs(Work w, ParamBlock<P> pb)
 #pragma unroll
         for (int i = 0; i < P::NQXX; i++) fd[(P::NX + i) * Bp] = cxx[i];
     }
-    if (!ok) atomicOr(&w.deriv_fail[b], 1);
+    if (!ok && fresh) atomicOr(&w.deriv_fail[b], 1);
 }
 
 /* =====================================================================================================================
