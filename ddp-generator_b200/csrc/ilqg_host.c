@@ -305,6 +305,10 @@ static chunk *ck_create(int device, int batch, int n_hor, int flags, void *strea
         return NULL;
     }
     h = (chunk *)calloc(1, sizeof *h);
+    if (!h) {
+        fail(NULL, "out of host memory");
+        return NULL;
+    }
     h->device = device;
     h->B = batch;
     h->total_B = batch;
@@ -320,6 +324,11 @@ static chunk *ck_create(int device, int batch, int n_hor, int flags, void *strea
         return NULL;
     }
     h->params = (double *)calloc((size_t)(h->d.npf > 0 ? h->d.npf : 1), sizeof(double));
+    if (!h->params) {
+        fail(NULL, "out of host memory");
+        free(h);
+        return NULL;
+    }
     ck_standard_parameters(h);
     if (stream) {
         h->stream = stream;
