@@ -90,7 +90,9 @@ int ilqgb_phase_linesearch(ilqgb_handle *h);
 /* field read-back (synchronises). Per-problem scalars: "cost" "new_cost" "dcost" "expected" "lambda" "dlambda"
  * "g_norm" "dV0" "dV1" "w_pen_l" "w_pen_f" -> [batch].  Trajectory fields, problem-major [batch][k][i]:
  * "x" "u" (nominal), "l" "L" "v1" (time-varying derivative entries) "v2" "fd" (final cx,cxx) "mu_f" "mu_r";
- * traces (ILQGB_TRACE): "tr_lambda" "tr_newcost" -> [batch][max_iter].  Returns doubles written, <0 on error. */
+ * traces (ILQGB_TRACE): "tr_lambda" "tr_newcost" -> [batch][max_iter].  Returns doubles written, <0 on error.
+ * "v1" "v2" "fd" hold the derivatives of the last sweep that covered the problem; for a problem that has finished they may
+ * have been re-evaluated at its final trajectory by a later sweep (they are never read again by the solver). */
 long ilqgb_get(ilqgb_handle *h, const char *field, double *out);
 /* "iterations" "result" "status" "n_linesearch" "n_backpass" "n_derivs" "n_rollouts" "n_tails" "cur" -> [batch]; "tr_alpha" -> [batch][max_iter];
  * "tr_clamp" -> [batch][n_hor] (2 bits per input: 0 free, 1 lower, 2 upper; QP return code in bits 16..23) */
