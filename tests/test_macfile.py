@@ -61,3 +61,22 @@ def test_own_mac_file_generates_and_compiles():
                             'template __global__ void ilqg::k_ls_round<ProbPendulum, false>(ilqg_work, ilqg_opts, ilqg::ParamBlock<ProbPendulum>, int, int);\n')
         subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-fmad=false", "-diag-suppress", "550,177,20281",
                         *inc, "-c", cu, "-o", os.path.join(d, "t.o")], check=True)
+
+
+def test_one_step_build_from_mac_file():
+    """python -m ilqg_gen.make: .mac file -> generated code -> loadable libraries (the role of the reference's make_iLQG.m)."""
+    import ctypes as C
+
+    from ilqg_gen import make
+
+    with tempfile.TemporaryDirectory() as d:
+        r = make.build(os.path.join(ROOT, "tests", "data", "pendulum.mac"), out=d)
+        assert r["name"] == "pendulum" and r["struct"] == "ProbPendulum" and all(os.path.exists(p) for p in r["libs"])
+        for ddp in (0, 1):
+            L = C.CDLL(os.path.join(d, "lib", f"libilqg_b200_pendulum_ddp{ddp}.so"))
+            L.ilqgb_problem_name.restype = C.c_char_p
+            L.ilqgb_param_name.restype = C.c_char_p
+            assert (L.ilqgb_nx(), L.ilqgb_nu(), L.ilqgb_full_ddp()) == (2, 1, ddp)
+            assert [L.ilqgb_param_name(i).decode() for i in range(L.ilqgb_n_params())] == ["b", "cu", "dt", "g", "l", "m", "q", "qf", "thg", "tmax"]
+        D = C.CDLL(os.path.join(d, "lib", "libilqg_dropin_pendulum_ddp0.so"))
+        assert all(hasattr(D, s) for s in ("iLQG", "setOptParam", "standard_parameters", "init_opt", "forward_pass", "makeCandidateNominal"))
