@@ -9,7 +9,9 @@ problem description -> generated code -> compiled libraries.
   libilqg_dropin_<name>_ddp{0,1}.so (the reference's single-problem entry points); both FULL_DDP settings are built,
   where the reference selects one with -DFULL_DDP (make_iLQG.m:2);
 * DIR defaults to the package directory (ddp-generator_b200/), which is where ilqg_b200.Library looks;
-* --flags are passed to nvcc (the reference's second argument: extra compiler switches).
+* --flags are passed to nvcc (the reference's second argument: extra compiler switches);
+* --mex additionally builds the MATLAB / Octave gateway mex/iLQG_mex_b200.c against the FULL_DDP=<d> library with `mkoctfile --mex`
+  (or `mex`), as make_iLQG.m:65-86 does for the reference; it needs one of the two on PATH.
 Needs nvcc (sm_100a cross-compiles without a GPU) and gcc; there is no Maxima / gentran step.
 """
 from __future__ import annotations
@@ -17,6 +19,7 @@ from __future__ import annotations
 import argparse
 import os
 import re
+import shutil
 import subprocess
 import sys
 
@@ -49,17 +52,35 @@ def build(source, name=None, out=None, flags="", jobs=8, quiet=True):
     return {"name": name, "struct": struct, "problem_dir": pdir, "libs": targets}
 
 
+def build_mex(name, full_ddp, out=None):
+    """The gateway as iLQG<Name>.mex / .mexa64 in DIR/lib (naming of make_iLQG.m:84)."""
+    out = os.path.abspath(out or PKG)
+    libdir = os.path.join(out, "lib")
+    tool = shutil.which("mkoctfile") or shutil.which("mex")
+    if not tool:
+        raise SystemExit("--mex needs mkoctfile (Octave) or mex (MATLAB) on PATH")
+    src = os.path.join(PKG, "mex", "iLQG_mex_b200.c")
+    target = os.path.join(libdir, f"iLQG{name.capitalize()}")
+    args = [tool] + (["--mex"] if tool.endswith("mkoctfile") else []) + [src, "-I" + os.path.join(os.path.dirname(PKG), "include"), "-L" + libdir,
+            f"-lilqg_b200_{name}_ddp{int(full_ddp)}", f"-Wl,-rpath,{libdir}", "-o" if tool.endswith("mkoctfile") else "-output", target]
+    subprocess.run(args, check=True)
+    return target
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(prog="python -m ilqg_gen.make", description=__doc__.split("\n\n")[0])
     ap.add_argument("source", help="problem.mac or a built-in problem name")
     ap.add_argument("--name", help="problem name (default: from the file name, optDefCar.mac -> car)")
     ap.add_argument("--out", help="output root (default: the package directory)")
     ap.add_argument("--flags", default="", help="extra nvcc flags")
+    ap.add_argument("--mex", type=int, choices=[0, 1], metavar="FULL_DDP", help="also build the mex gateway against the FULL_DDP=0|1 library")
     a = ap.parse_args(argv)
     r = build(a.source, a.name, a.out, a.flags, quiet=False)
     print(f"problem {r['name']} ({r['struct']}): code in {r['problem_dir']}")
     for l in r["libs"]:
         print("  ", l)
+    if a.mex is not None:
+        print("  ", build_mex(r["name"], a.mex, a.out))
 
 
 if __name__ == "__main__":
