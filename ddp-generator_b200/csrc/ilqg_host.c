@@ -862,8 +862,11 @@ struct ilqgb_handle {
 
 static int auto_chunks(int batch)
 {
-    int n = batch / 32768;   /* keep >= 32768 problems (1024 warps) per chunk so each kernel still fills the GPU */
-    if (n < 1) n = 1;
+    /* measured on B200 (bench.py --batch B --chunks n, car): 32 768 problems: 1 chunk (2 are 4 % faster resident but slower end to
+       end); 65 536: 2 chunks 6.80 M it/s, 1 chunk 6.64 M; 131 072: 2 chunks 7.43 M, 4 chunks 7.30 M; 262 144: 4 chunks (6, 8, 12 are
+       slower).  So: chunks of about 65 536 problems, at least two once there are 65 536, at most four. */
+    int n = batch / 65536;
+    if (n < 2) n = batch >= 65536 ? 2 : 1;
     if (n > 4) n = 4;
     return n;
 }
