@@ -80,3 +80,38 @@ def test_one_step_build_from_mac_file():
             assert [L.ilqgb_param_name(i).decode() for i in range(L.ilqgb_n_params())] == ["b", "cu", "dt", "g", "l", "m", "q", "qf", "thg", "tmax"]
         D = C.CDLL(os.path.join(d, "lib", "libilqg_dropin_pendulum_ddp0.so"))
         assert all(hasattr(D, s) for s in ("iLQG", "setOptParam", "standard_parameters", "init_opt", "forward_pass", "makeCandidateNominal"))
+
+
+_BAD = """x: [p, v];
+u: [a, w];
+f[p]: p + dt*v;
+f[v]: v + dt*a;
+L: a^2 + w^2;
+F: p^2;
+%s
+"""
+
+
+@pytest.mark.parametrize("h,msg", [
+    ("h[1]: a + w - 1;", "may depend on only one input"),              # genenerator_main.mac:389-390
+    ("h[1]: 2*a - 1;", "must be 1 or -1"),                             # genenerator_main.mac:392-393
+    ("h[1]: a + a^2 - 1;", "must be 1 or -1"),
+    ("s: a*v;\nh[1]: w + 's - 1;", "may depend on only one input|may only depend directly on one input"),   # a second input through an aux value (:386-391)
+])
+def test_invalid_input_constraints_are_rejected_like_the_reference_generator(h, msg):
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "optDefBad.mac")
+        open(path, "w").write(_BAD % h)
+        with pytest.raises(ValueError, match=msg):
+            lower(load_mac(path))
+
+
+def test_f_must_be_indexed_by_states_and_k_index_cannot_be_mixed():
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "optDefBad.mac")
+        open(path, "w").write(_BAD.replace("f[v]:", "f[q]:") % "")
+        with pytest.raises(ValueError, match="indexed by elements of x"):
+            load_mac(path)
+        open(path, "w").write(_BAD.replace("L: a^2 + w^2;", "L: r[k]*a^2 + r[1]*w^2;") % "")
+        with pytest.raises(ValueError, match="index k and other integer index mixed"):      # genenerator_main.mac:146-152
+            load_mac(path)
