@@ -16,6 +16,7 @@ using P = ILQG_PROBLEM_STRUCT;
 using namespace ilqg;
 
 static thread_local char g_err[256] = "";
+#define ILQGK_MAX_DEVICES 64
 
 static int check(cudaError_t e, const char *what)
 {
@@ -58,12 +59,36 @@ int ilqgk_host_free(void *p) { return p ? check(cudaFreeHost(p), "cudaFreeHost")
 int ilqgk_memset(void *p, int v, size_t bytes, void *stream) { return check(cudaMemsetAsync(p, v, bytes, (cudaStream_t)stream), "cudaMemsetAsync"); }
 int ilqgk_h2d(void *dst, const void *src, size_t bytes, void *stream) { return check(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream), "H2D"); }
 int ilqgk_d2h(void *dst, const void *src, size_t bytes, void *stream) { return check(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream), "D2H"); }
+int ilqgk_d2d(void *dst, const void *src, size_t bytes, void *stream) { return check(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream), "D2D"); }
 int ilqgk_stream_create(void **s) { cudaStream_t st; int r = check(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "cudaStreamCreate"); *s = (void *)st; return r; }
+int ilqgk_stream_create_prio(void **s, int rank, int n_ranks)
+{
+    /* rank 0 = most urgent of n_ranks; mapped onto the device's priority range (numerically lower = more urgent) */
+    int least = 0, greatest = 0, levels, prio;
+    cudaStream_t st;
+    if (check(cudaDeviceGetStreamPriorityRange(&least, &greatest), "cudaDeviceGetStreamPriorityRange")) return -1;
+    levels = least - greatest + 1;
+    if (levels < 1) levels = 1;
+    prio = n_ranks > 1 ? greatest + (int)((long long)rank * levels / n_ranks) : least;
+    if (prio > least) prio = least;
+    int r = check(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio), "cudaStreamCreateWithPriority");
+    *s = (void *)st;
+    return r;
+}
 int ilqgk_stream_destroy(void *s) { return check(cudaStreamDestroy((cudaStream_t)s), "cudaStreamDestroy"); }
 int ilqgk_stream_sync(void *s) { return check(cudaStreamSynchronize((cudaStream_t)s), "cudaStreamSynchronize"); }
 int ilqgk_event_create(void **e) { cudaEvent_t ev; int r = check(cudaEventCreate(&ev), "cudaEventCreate"); *e = (void *)ev; return r; }
 int ilqgk_event_create_notiming(void **e) { cudaEvent_t ev; int r = check(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreate"); *e = (void *)ev; return r; }
 int ilqgk_stream_wait_event(void *s, void *e) { return check(cudaStreamWaitEvent((cudaStream_t)s, (cudaEvent_t)e, 0), "cudaStreamWaitEvent"); }
+int ilqgk_event_query(void *e)
+{
+    /* 1 = complete, 0 = still pending, -1 = error */
+    const cudaError_t r = cudaEventQuery((cudaEvent_t)e);
+    if (r == cudaSuccess) return 1;
+    if (r == cudaErrorNotReady) return 0;
+    return check(r, "cudaEventQuery");
+}
+int ilqgk_event_sync(void *e) { return check(cudaEventSynchronize((cudaEvent_t)e), "cudaEventSynchronize"); }
 int ilqgk_event_destroy(void *e) { return check(cudaEventDestroy((cudaEvent_t)e), "cudaEventDestroy"); }
 int ilqgk_event_record(void *e, void *s) { return check(cudaEventRecord((cudaEvent_t)e, (cudaStream_t)s), "cudaEventRecord"); }
 int ilqgk_event_elapsed(void *a, void *b, float *ms) { return check(cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b), "cudaEventElapsedTime"); }
@@ -101,13 +126,17 @@ int ilqgk_launch_backpass(const ilqg_work *w, const ilqg_opts *o, const double *
         PP_DISPATCH(w, (k_backpass_warp<P, FULL_DDP != 0, PP><<<nblk(w->B, CW_WARPS), CW_WARPS * 32, 0, (cudaStream_t)stream>>>(*w, *o, make_pb(params), iter)));
     else {
         constexpr size_t smem = sizeof(double) * 2 * bp_fields<P, FULL_DDP != 0>() * BP_BLOCK;
-        static bool configured = false;
-        if (!configured) {
+        /* the opt-in to > 48 KB dynamic shared memory is a per-device function attribute: applied once on every device
+           this process launches on (idempotent, so two threads racing on the same device are harmless) */
+        static unsigned char configured[ILQGK_MAX_DEVICES];
+        int dev = 0;
+        if (check(cudaGetDevice(&dev), "cudaGetDevice")) return -1;
+        if (dev < 0 || dev >= ILQGK_MAX_DEVICES || !configured[dev]) {
             if (check(cudaFuncSetAttribute(k_backpass<P, FULL_DDP != 0, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return -1;
             if (check(cudaFuncSetAttribute(k_backpass<P, FULL_DDP != 0, ILQG_BP_MINBLOCKS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return -1;
             if (check(cudaFuncSetAttribute(k_backpass<P, FULL_DDP != 0, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return -1;
             if (check(cudaFuncSetAttribute(k_backpass<P, FULL_DDP != 0, ILQG_BP_MINBLOCKS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return -1;
-            configured = true;
+            if (dev >= 0 && dev < ILQGK_MAX_DEVICES) configured[dev] = 1;
         }
         if (o->bp_latency_build)
             PP_DISPATCH(w, (k_backpass<P, FULL_DDP != 0, 1, PP><<<nblk(w->B, BP_BLOCK), BP_BLOCK, smem, (cudaStream_t)stream>>>(*w, *o, make_pb(params), iter)));

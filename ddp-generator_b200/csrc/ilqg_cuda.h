@@ -28,12 +28,16 @@ int ilqgk_host_free(void *p);
 int ilqgk_memset(void *p, int v, size_t bytes, void *stream);
 int ilqgk_h2d(void *dst, const void *src, size_t bytes, void *stream);
 int ilqgk_d2h(void *dst, const void *src, size_t bytes, void *stream);
+int ilqgk_d2d(void *dst, const void *src, size_t bytes, void *stream);
 int ilqgk_stream_create(void **s);
+int ilqgk_stream_create_prio(void **s, int rank, int n_ranks); /* rank 0 = most urgent of n_ranks */
 int ilqgk_stream_destroy(void *s);
 int ilqgk_stream_sync(void *s);
 int ilqgk_event_create(void **e);
 int ilqgk_event_create_notiming(void **e);
 int ilqgk_stream_wait_event(void *s, void *e);
+int ilqgk_event_query(void *e); /* 1 complete, 0 pending, -1 error */
+int ilqgk_event_sync(void *e);
 int ilqgk_event_destroy(void *e);
 int ilqgk_event_record(void *e, void *s);
 int ilqgk_event_elapsed(void *a, void *b, float *ms);

@@ -6,8 +6,10 @@
  * (lambda schedule, accept/reject, termination) lives in per-problem device state, so ragged convergence needs no
  * host round trip per pass.  All problems that are still running are at the same pass index `iter`.
  */
+#define _POSIX_C_SOURCE 200809L
 #include <stdio.h>
 #include <stdlib.h>
+#include <time.h>
 #include <string.h>
 #include <math.h>
 
@@ -15,6 +17,9 @@
 #include "ilqg_cuda.h"
 
 #define ACTIVE_CHECK_EVERY 8
+#define POLL_RING 4          /* progress polls a chunk may have in flight (engine look-ahead is 2 blocks of passes) */
+#define ENGINE_BLOCK 8       /* passes issued per chunk between two progress polls */
+#define ENGINE_LOOKAHEAD 2
 enum { TC_DERIVS = 0, TC_BACKPASS = 1, TC_LINESEARCH = 2, TC_POST = 3, TC_N = 4 };
 
 typedef struct {
@@ -32,9 +37,17 @@ struct chunk {
     double *d_kp[16];      /* [k]-indexed parameters: device arrays of n_hor + 1 doubles, in parameter order */
     double **d_pk;         /* device table of those pointers (ilqg_work.pk) */
     double *d_pp;          /* per-problem parameter sets [npf][Bp] (ilqg_work.pp), allocated on first use */
-    void *stream;
+    void *stream;          /* the stream all work of this chunk is enqueued on (stream_main, or stream_io during an end-to-end solve) */
+    void *stream_main, *stream_io;
     int owns_stream;
+    int prio_rank, prio_n; /* position of this chunk among the chunks of its device (stream_io priority) */
     int iter;              /* pass index of the running problems */
+    /* asynchronous solve engine (run_engine): progress polls in flight, early stop, gating */
+    int *h_poll;           /* pinned ring of POLL_RING running-problem counts */
+    void *ev_poll[4];
+    int poll_issued, poll_seen, stop, phase;
+    void *ev_gate;
+    int gate_recorded;
     int ls_tail_from;      /* -1 = choose by batch size */
     int bp_latency;        /* -1 = choose by batch size */
     int total_B;           /* problems of the whole handle (all chunks run concurrently on one GPU) */
@@ -73,11 +86,31 @@ static void *dalloc(chunk *h, size_t bytes)
         return NULL;
     }
     if (h->n_allocs == h->cap_allocs) {
-        h->cap_allocs = h->cap_allocs ? 2 * h->cap_allocs : 64;
-        h->allocs = (void **)realloc(h->allocs, sizeof(void *) * h->cap_allocs);
+        const int cap = h->cap_allocs ? 2 * h->cap_allocs : 64;
+        void **a = (void **)realloc(h->allocs, sizeof(void *) * cap);
+        if (!a) {
+            ilqgk_free(p);
+            fail(h, "out of host memory");
+            return NULL;
+        }
+        h->allocs = a;
+        h->cap_allocs = cap;
     }
     h->allocs[h->n_allocs++] = p;
     return p;
+}
+
+/* release one device allocation made by dalloc before the handle goes away */
+static void dfree(chunk *h, void *p)
+{
+    int i;
+    if (!p) return;
+    for (i = 0; i < h->n_allocs; i++)
+        if (h->allocs[i] == p) {
+            h->allocs[i] = h->allocs[--h->n_allocs];
+            break;
+        }
+    ilqgk_free(p);
 }
 
 /* ---- static facts -------------------------------------------------------------------------------------------------- */
@@ -221,6 +254,7 @@ static int pp_fill_row(chunk *h, int row, double v)
     size_t b;
     double *tmp = (double *)malloc(sizeof(double) * h->Bp);
     int rc;
+    if (!tmp) return fail(h, "out of host memory");
     for (b = 0; b < (size_t)h->Bp; b++) tmp[b] = v;
     rc = ilqgk_h2d(h->d_pp + (size_t)row * h->Bp, tmp, sizeof(double) * h->Bp, h->stream) || ilqgk_stream_sync(h->stream);
     free(tmp);
@@ -247,6 +281,7 @@ static int ck_set_param_batch(chunk *h, int index, const double *value, int n)
     }
     off = param_offset(index);
     tmp = (double *)calloc((size_t)h->Bp, sizeof(double));
+    if (!tmp) return fail(h, "out of host memory");
     for (i = 0; i < n; i++) {
         for (b = 0; b < (size_t)h->B; b++) tmp[b] = value[b * n + i];
         if (ilqgk_h2d(h->d_pp + (size_t)(off + i) * h->Bp, tmp, sizeof(double) * h->Bp, h->stream) || ilqgk_stream_sync(h->stream)) {
@@ -288,7 +323,7 @@ static int ck_set_param(chunk *h, int index, const double *value, int n)
         if (!(dst)) goto oom;                                      \
     } while (0)
 
-static chunk *ck_create(int device, int batch, int n_hor, int flags, void *stream)
+static chunk *ck_create(int device, int batch, int n_hor, int flags, void *stream, int prio_rank, int prio_n)
 {
     chunk *h;
     size_t Bp, T = (size_t)n_hor;
@@ -330,12 +365,15 @@ static chunk *ck_create(int device, int batch, int n_hor, int flags, void *strea
         return NULL;
     }
     ck_standard_parameters(h);
+    h->prio_rank = prio_rank;
+    h->prio_n = prio_n;
     if (stream) {
-        h->stream = stream;
+        h->stream_main = stream;
     } else {
-        if (ilqgk_stream_create(&h->stream)) goto oom;
+        if (ilqgk_stream_create(&h->stream_main)) goto oom;
         h->owns_stream = 1;
     }
+    h->stream = h->stream_main;
     Bp = (size_t)h->Bp;
     {
         const ilqgk_dims_t *d = &h->d;
@@ -405,6 +443,13 @@ static chunk *ck_create(int device, int batch, int n_hor, int flags, void *strea
         DALLOC(h->d_counter, int, 1);
     }
     if (ilqgk_host_alloc((void **)&h->h_counter, sizeof(int))) goto oom;
+    if (ilqgk_host_alloc((void **)&h->h_poll, sizeof(int) * POLL_RING)) goto oom;
+    {
+        int i;
+        for (i = 0; i < POLL_RING; i++)
+            if (ilqgk_event_create_notiming(&h->ev_poll[i])) goto oom;
+        if (ilqgk_event_create_notiming(&h->ev_gate)) goto oom;
+    }
     return h;
 oom:
     snprintf(g_create_err, sizeof g_create_err, "%s", h->err[0] ? h->err : ilqgk_last_error());
@@ -417,7 +462,12 @@ static void ck_destroy(chunk *h)
     int i;
     if (!h) return;
     ilqgk_set_device(h->device);
-    if (h->stream) ilqgk_stream_sync(h->stream);
+    if (h->stream_main) ilqgk_stream_sync(h->stream_main);
+    if (h->stream_io) ilqgk_stream_sync(h->stream_io);
+    for (i = 0; i < POLL_RING; i++)
+        if (h->ev_poll[i]) ilqgk_event_destroy(h->ev_poll[i]);
+    if (h->ev_gate) ilqgk_event_destroy(h->ev_gate);
+    if (h->h_poll) ilqgk_host_free(h->h_poll);
     for (i = 0; i < h->n_allocs; i++) ilqgk_free(h->allocs[i]);
     free(h->allocs);
     for (i = 0; i < h->n_ev_created; i++) {
@@ -426,7 +476,8 @@ static void ck_destroy(chunk *h)
     }
     free(h->ev);
     if (h->h_counter) ilqgk_host_free(h->h_counter);
-    if (h->owns_stream && h->stream) ilqgk_stream_destroy(h->stream);
+    if (h->stream_io) ilqgk_stream_destroy(h->stream_io);
+    if (h->owns_stream && h->stream_main) ilqgk_stream_destroy(h->stream_main);
     free(h->params);
     free(h);
 }
@@ -434,7 +485,12 @@ static void ck_destroy(chunk *h)
 static int ensure_stage(chunk *h, size_t doubles)
 {
     if (doubles <= h->stage_doubles) return 0;
-    /* the old staging buffer stays in the allocation list and is freed with the handle */
+    if (h->d_stage) { /* work that still reads the old buffer is ordered before its release (cudaFree synchronises) */
+        if (ilqgk_stream_sync(h->stream)) return failk(h);
+        dfree(h, h->d_stage);
+        h->d_stage = NULL;
+        h->stage_doubles = 0;
+    }
     h->d_stage = (double *)dalloc(h, sizeof(double) * doubles);
     if (!h->d_stage) {
         h->stage_doubles = 0;
@@ -446,15 +502,32 @@ static int ensure_stage(chunk *h, size_t doubles)
 
 static int ensure_traces(chunk *h)
 {
-    size_t n;
+    size_t n, n_old;
     const int need = h->o.max_iter > 0 ? h->o.max_iter : 1;
+    double *lam, *nc, *z;
+    int *al;
     if (!(h->flags & ILQGB_TRACE) || need <= h->trace_cap) return 0;
     n = (size_t)need * h->Bp;
-    h->w.tr_lambda = (double *)dalloc(h, sizeof(double) * n);
-    h->w.tr_newcost = (double *)dalloc(h, sizeof(double) * n);
-    h->w.tr_alpha = (int *)dalloc(h, sizeof(int) * n);
-    h->w.tr_z = (double *)dalloc(h, sizeof(double) * n);
-    if (!h->w.tr_lambda || !h->w.tr_newcost || !h->w.tr_alpha || !h->w.tr_z) return -1;
+    n_old = (size_t)h->trace_cap * h->Bp;
+    lam = (double *)dalloc(h, sizeof(double) * n);
+    nc = (double *)dalloc(h, sizeof(double) * n);
+    al = (int *)dalloc(h, sizeof(int) * n);
+    z = (double *)dalloc(h, sizeof(double) * n);
+    if (!lam || !nc || !al || !z) return -1;
+    if (n_old) { /* max_iter was raised after the traces were sized (possibly mid-solve): keep what has been recorded */
+        if (ilqgk_d2d(lam, h->w.tr_lambda, sizeof(double) * n_old, h->stream) || ilqgk_d2d(nc, h->w.tr_newcost, sizeof(double) * n_old, h->stream) ||
+            ilqgk_d2d(al, h->w.tr_alpha, sizeof(int) * n_old, h->stream) || ilqgk_d2d(z, h->w.tr_z, sizeof(double) * n_old, h->stream) ||
+            ilqgk_stream_sync(h->stream))
+            return failk(h);
+        dfree(h, h->w.tr_lambda);
+        dfree(h, h->w.tr_newcost);
+        dfree(h, h->w.tr_alpha);
+        dfree(h, h->w.tr_z);
+    }
+    h->w.tr_lambda = lam;
+    h->w.tr_newcost = nc;
+    h->w.tr_alpha = al;
+    h->w.tr_z = z;
     h->trace_cap = need;
     return 0;
 }
@@ -545,8 +618,11 @@ static ev_pair *timing_begin(chunk *h, int cls)
     ev_pair *p;
     if (!(h->flags & ILQGB_TIMING)) return NULL;
     if (h->n_ev == h->cap_ev) {
-        h->cap_ev = h->cap_ev ? 2 * h->cap_ev : 256;
-        h->ev = (ev_pair *)realloc(h->ev, sizeof(ev_pair) * h->cap_ev);
+        const int cap = h->cap_ev ? 2 * h->cap_ev : 256;
+        ev_pair *e = (ev_pair *)realloc(h->ev, sizeof(ev_pair) * cap);
+        if (!e) return NULL; /* out of host memory: this launch goes untimed */
+        h->ev = e;
+        h->cap_ev = cap;
     }
     p = &h->ev[h->n_ev];
     if (h->n_ev == h->n_ev_created) {
@@ -608,6 +684,7 @@ static int ck_start(chunk *h)
 static int launch_pass(chunk *h, int do_derivs, int do_back, int do_ls)
 {
     ev_pair *p;
+    if (ensure_traces(h)) return -1;   /* max_iter may have been raised since the solve started */
     if (do_derivs) {
         p = timing_begin(h, TC_DERIVS);
         if (ilqgk_launch_derivs(&h->w, h->params, h->stream)) return failk(h);
@@ -796,6 +873,7 @@ static long ck_get_int(chunk *h, const char *f, int *out)
         /* small, test-only path: copy [n_k][Bp] and transpose on the host */
         int *tmp = (int *)malloc(sizeof(int) * n_k * Bp);
         size_t b, k;
+        if (!tmp) return fail(h, "out of host memory");
         if (ilqgk_d2h(tmp, arr, sizeof(int) * n_k * Bp, h->stream) || ilqgk_stream_sync(h->stream)) {
             free(tmp);
             return failk(h);
@@ -847,26 +925,33 @@ static int ck_rollout(chunk *h, double alpha, int cost_only)
  * one chunk (late line-search rounds with few undecided problems) with the wide kernels of another, and uploads /
  * downloads of one chunk with the compute of the others.  Work enqueued by one API call is ordered in the handle's
  * main stream: chunk streams fork from it at entry and join it at exit.
+ *
+ * A handle may span several GPUs (ilqgb_create_multi): the batch is cut into one contiguous shard per device
+ * (no exchange step, one final host-side gather) and every shard into chunks as above; one host thread
+ * drives all devices, which works because nothing below ever blocks on a single chunk.
  * ===================================================================================================================== */
-#define MAX_CHUNKS 16
+#define MAX_CHUNKS 64
+#define MAX_DEVICES 16
 struct ilqgb_handle {
     int n, device, B, T, flags;
+    int n_dev, devices[MAX_DEVICES];
     chunk *c[MAX_CHUNKS];
     int first[MAX_CHUNKS];
-    void *stream;      /* main stream (caller's or owned) */
+    void *stream;      /* main stream (caller's or owned), on devices[0] */
     int owns_stream;
     void *ev_fork, *ev_join[MAX_CHUNKS];
+    int e2e_prio, e2e_stagger;   /* end-to-end solve: chunk streams with descending priority; start gate in passes */
     ilqgk_dims_t d;
     char err[256];
 };
 
 static int auto_chunks(int batch)
 {
-    /* measured on B200 (bench.py --batch B --chunks n, car): 32 768 problems: 1 chunk (2 are 4 % faster resident but slower end to
-       end); 65 536: 2 chunks 6.80 M it/s, 1 chunk 6.64 M; 131 072: 2 chunks 7.43 M, 4 chunks 7.30 M; 262 144: 4 chunks (6, 8, 12 are
-       slower).  So: chunks of about 65 536 problems, at least two once there are 65 536, at most four. */
+    /* measured on B200 (bench.py --batch B --chunks n, car): chunks of about 65 536 problems, at least two once there are
+       65 536, at most four (262 144: 6, 8, 12 chunks are slower for a resident solve).  Smaller batches still get two chunks
+       from 16 384 problems on, so that an end-to-end solve has something to overlap its copies with. */
     int n = batch / 65536;
-    if (n < 2) n = batch >= 65536 ? 2 : 1;
+    if (n < 2) n = batch >= 16384 ? 2 : 1;
     if (n > 4) n = 4;
     return n;
 }
@@ -880,47 +965,75 @@ static int hfail(ilqgb_handle *h, const chunk *c)
 static int fork_streams(ilqgb_handle *h)
 {
     int i;
-    if (h->n == 1) return 0;
+    if (h->n == 1 && h->c[0]->stream == h->stream) return 0;
+    if (ilqgk_set_device(h->device)) return hfail(h, NULL);
     if (ilqgk_event_record(h->ev_fork, h->stream)) return hfail(h, NULL);
-    for (i = 0; i < h->n; i++)
+    for (i = 0; i < h->n; i++) {
+        if (ilqgk_set_device(h->c[i]->device)) return hfail(h, NULL);
         if (ilqgk_stream_wait_event(h->c[i]->stream, h->ev_fork)) return hfail(h, NULL);
+    }
     return 0;
 }
 
 static int join_streams(ilqgb_handle *h)
 {
     int i;
-    if (h->n == 1) return 0;
+    if (h->n == 1 && h->c[0]->stream == h->stream) return 0;
     for (i = 0; i < h->n; i++) {
+        if (ilqgk_set_device(h->c[i]->device)) return hfail(h, NULL);
         if (ilqgk_event_record(h->ev_join[i], h->c[i]->stream)) return hfail(h, NULL);
-        if (ilqgk_stream_wait_event(h->stream, h->ev_join[i])) return hfail(h, NULL);
     }
+    if (ilqgk_set_device(h->device)) return hfail(h, NULL);
+    for (i = 0; i < h->n; i++)
+        if (ilqgk_stream_wait_event(h->stream, h->ev_join[i])) return hfail(h, NULL);
     return 0;
 }
 
 const char *ilqgb_last_error(const ilqgb_handle *h) { return h ? h->err : g_create_err; }
 
-ilqgb_handle *ilqgb_create(int device, int batch, int n_hor, int flags, void *stream)
+static int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+ilqgb_handle *ilqgb_create_multi(int n_devices, const int *devices, int batch, int n_hor, int flags, void *stream)
 {
     ilqgb_handle *h;
-    int i, n = (flags >> 8) & 0xff, per;
+    int d, n_req = (flags >> 8) & 0xff, n_total = 0;
     if (batch < 1 || n_hor < 1) {
         fail_create("batch and n_hor must be >= 1");
         return NULL;
     }
-    if (n == 0) n = auto_chunks(batch);
-    if (n > MAX_CHUNKS) n = MAX_CHUNKS;
-    if (n > batch) n = batch;
+    if (n_devices < 1 || n_devices > MAX_DEVICES) {
+        fail_create("n_devices out of range");
+        return NULL;
+    }
     if (ilqgk_device_count() < 1) {
         fail_create("no CUDA device available: this library has no CPU fallback");
         return NULL;
     }
-    if (ilqgk_set_device(device)) {
+    for (d = 0; d < n_devices; d++)
+        if ((devices ? devices[d] : d) < 0 || (devices ? devices[d] : d) >= ilqgk_device_count()) {
+            fail_create("device index out of range");
+            return NULL;
+        }
+    if (n_devices > batch) n_devices = batch;
+    if (ilqgk_set_device(devices ? devices[0] : 0)) {
         fail_create(ilqgk_last_error());
         return NULL;
     }
     h = (ilqgb_handle *)calloc(1, sizeof *h);
-    h->n = n; h->device = device; h->B = batch; h->T = n_hor; h->flags = flags;
+    if (!h) {
+        fail_create("out of host memory");
+        return NULL;
+    }
+    h->n_dev = n_devices;
+    for (d = 0; d < n_devices; d++) h->devices[d] = devices ? devices[d] : d;
+    h->device = h->devices[0];
+    h->B = batch; h->T = n_hor; h->flags = flags;
+    h->e2e_prio = env_int("ILQG_E2E_PRIO", 1);
+    h->e2e_stagger = env_int("ILQG_E2E_STAGGER", 0);
     ilqgk_dims(&h->d);
     if (stream) {
         h->stream = stream;
@@ -928,22 +1041,46 @@ ilqgb_handle *ilqgb_create(int device, int batch, int n_hor, int flags, void *st
         if (ilqgk_stream_create(&h->stream)) { fail_create(ilqgk_last_error()); free(h); return NULL; }
         h->owns_stream = 1;
     }
-    per = ((batch + n - 1) / n + 31) / 32 * 32;   /* chunk sizes are multiples of a warp */
-    for (i = 0; i < n; i++) {
-        const int first = i * per;
-        int cnt = batch - first < per ? batch - first : per;
-        if (cnt <= 0) { h->n = i; break; }
-        h->first[i] = first;
-        h->c[i] = ck_create(device, cnt, n_hor, flags & 0xff, n == 1 ? h->stream : NULL);
-        if (!h->c[i]) { ilqgb_destroy(h); return NULL; }
-        h->c[i]->total_B = batch;
+    for (d = 0; d < n_devices; d++) {
+        /* contiguous shard of device d, then its chunks (sizes are multiples of a warp; the final chunk count is fixed
+           before any chunk is created, so a single chunk runs on the handle's own stream) */
+        const int sfirst = (int)((long long)batch * d / n_devices), scount = (int)((long long)batch * (d + 1) / n_devices) - sfirst;
+        int n = n_req ? n_req : auto_chunks(scount), per, i, made = 0;
+        if (n > scount) n = scount;
+        per = ((scount + n - 1) / n + 31) / 32 * 32;
+        n = (scount + per - 1) / per;
+        if (n_total + n > MAX_CHUNKS) n = MAX_CHUNKS - n_total;
+        if (n < 1) { fail_create("too many chunks"); ilqgb_destroy(h); return NULL; }
+        per = ((scount + n - 1) / n + 31) / 32 * 32;
+        for (i = 0; i < n; i++) {
+            const int first = i * per;
+            const int cnt = scount - first < per ? scount - first : per;
+            chunk *c;
+            if (cnt <= 0) break;
+            c = ck_create(h->devices[d], cnt, n_hor, flags & 0xff, (n == 1 && n_devices == 1) ? h->stream : NULL, i, n);
+            if (!c) { ilqgb_destroy(h); return NULL; }
+            c->total_B = scount;
+            h->first[n_total + made] = sfirst + first;
+            h->c[n_total + made] = c;
+            made++;
+        }
+        n_total += made;
     }
-    if (h->n > 1) {
-        if (ilqgk_event_create_notiming(&h->ev_fork)) { fail_create(ilqgk_last_error()); ilqgb_destroy(h); return NULL; }
-        for (i = 0; i < h->n; i++)
-            if (ilqgk_event_create_notiming(&h->ev_join[i])) { fail_create(ilqgk_last_error()); ilqgb_destroy(h); return NULL; }
-    }
+    h->n = n_total;
+    if (ilqgk_set_device(h->device) || ilqgk_event_create_notiming(&h->ev_fork)) { fail_create(ilqgk_last_error()); ilqgb_destroy(h); return NULL; }
+    for (d = 0; d < h->n; d++)
+        if (ilqgk_set_device(h->c[d]->device) || ilqgk_event_create_notiming(&h->ev_join[d])) { fail_create(ilqgk_last_error()); ilqgb_destroy(h); return NULL; }
+    ilqgk_set_device(h->device);
     return h;
+}
+
+ilqgb_handle *ilqgb_create(int device, int batch, int n_hor, int flags, void *stream)
+{
+    if (device < 0) {
+        fail_create("device index out of range");
+        return NULL;
+    }
+    return ilqgb_create_multi(1, &device, batch, n_hor, flags, stream);
 }
 
 void ilqgb_destroy(ilqgb_handle *h)
@@ -951,13 +1088,17 @@ void ilqgb_destroy(ilqgb_handle *h)
     int i;
     if (!h) return;
     for (i = 0; i < MAX_CHUNKS; i++) {
-        if (h->c[i]) ck_destroy(h->c[i]);
+        if (h->c[i]) ilqgk_set_device(h->c[i]->device);
         if (h->ev_join[i]) ilqgk_event_destroy(h->ev_join[i]);
+        if (h->c[i]) ck_destroy(h->c[i]);
     }
+    ilqgk_set_device(h->device);
     if (h->ev_fork) ilqgk_event_destroy(h->ev_fork);
     if (h->owns_stream && h->stream) ilqgk_stream_destroy(h->stream);
     free(h);
 }
+
+int ilqgb_devices(const ilqgb_handle *h) { return h->n_dev; }
 
 void ilqgb_standard_parameters(ilqgb_handle *h) { int i; for (i = 0; i < h->n; i++) ck_standard_parameters(h->c[i]); }
 
@@ -1028,20 +1169,26 @@ int ilqgb_active(ilqgb_handle *h)
     return tot;
 }
 
+/* passes of the loop for every chunk in lock step (the stepwise API: a caller can look at the state between calls) */
 int ilqgb_iterate(ilqgb_handle *h, int n_passes)
 {
     int done = 0, i;
-    chunk *c0 = h->c[0];
-    if (!c0->started) { snprintf(h->err, sizeof h->err, "ilqgb_start has not been called"); return -1; }
-    if (ilqgk_set_device(h->device)) return hfail(h, NULL);
+    for (i = 0; i < h->n; i++)
+        if (!h->c[i]->started) { snprintf(h->err, sizeof h->err, "ilqgb_start has not been called"); return -1; }
     if (fork_streams(h)) return -1;
-    while (done < n_passes && c0->iter < c0->o.max_iter) {
+    while (done < n_passes) {
+        int launched = 0;
         for (i = 0; i < h->n; i++) {   /* issue pass p of every chunk before pass p+1 of any: streams advance together */
-            if (launch_pass(h->c[i], 1, 1, 1)) return hfail(h, h->c[i]);
-            h->c[i]->iter++;
+            chunk *c = h->c[i];
+            if (c->iter >= c->o.max_iter) continue;
+            if (ilqgk_set_device(c->device)) return hfail(h, NULL);
+            if (launch_pass(c, 1, 1, 1)) return hfail(h, c);
+            c->iter++;
+            launched = 1;
         }
+        if (!launched) break;
         done++;
-        if (c0->iter % ACTIVE_CHECK_EVERY == 0 && c0->iter < c0->o.max_iter) {
+        if (done % ACTIVE_CHECK_EVERY == 0 && done < n_passes) {
             const int a = ilqgb_active(h);
             if (a < 0) return -1;
             if (a == 0) break;
@@ -1060,62 +1207,140 @@ int ilqgb_finish(ilqgb_handle *h)
     return join_streams(h);
 }
 
-int ilqgb_solve(ilqgb_handle *h)
+/* ---- asynchronous solve engine -----------------------------------------------------------------------------------------
+ * Every chunk runs its whole solve (optionally framed by its upload and its download) on its own stream; the host
+ * never waits for a particular chunk.  Passes are issued in blocks of ENGINE_BLOCK per chunk, at most ENGINE_LOOKAHEAD
+ * blocks ahead of the last block known to have completed; each block ends with a count of the problems still
+ * running, copied to pinned memory and polled with cudaEventQuery, so a chunk whose problems have all finished stops
+ * being issued (ragged convergence) without a host synchronisation.
+ * End to end (`io`): uploads are queued first, in chunk order; with e2e_prio the chunk streams carry descending
+ * priorities, so the chunks FINISH one after the other instead of all at once and the result copies of chunk i
+ * overlap the passes of chunks i+1.. (the copy engines and both PCIe directions stay busy while the SMs do);
+ * e2e_stagger additionally holds chunk i back until chunk i-1 of its device has issued that many passes. */
+typedef struct {
+    const double *x0, *u_nom;
+    double *x, *u, *cost;
+    int *iterations, *result, *n_linesearch;
+} io_t;
+
+static int engine_poll(chunk *c)
 {
-    int i;
-    if (ilqgb_start(h)) return -1;
-    while (h->c[0]->iter < h->c[0]->o.max_iter) {
-        const int n = ilqgb_iterate(h, h->c[0]->o.max_iter - h->c[0]->iter);
-        if (n < 0) return -1;
-        if (h->c[0]->iter < h->c[0]->o.max_iter && ilqgb_active(h) == 0) break;
+    while (c->poll_seen < c->poll_issued) {
+        const int slot = c->poll_seen % POLL_RING;
+        const int q = ilqgk_event_query(c->ev_poll[slot]);
+        if (q < 0) return failk(c);
+        if (q == 0) break;
+        if (c->h_poll[slot] == 0) c->stop = 1;
+        c->poll_seen++;
     }
-    if (fork_streams(h)) return -1;
-    for (i = 0; i < h->n; i++)   /* problems still running after the last pass hit the iteration limit */
-        if (ilqgk_launch_finalize(&h->c[i]->w, h->c[i]->o.max_iter, h->c[i]->stream)) return hfail(h, NULL);
-    return join_streams(h);
+    return 0;
 }
 
-/* End to end from and to host buffers (pinned for full overlap): every chunk uploads, solves and downloads on its own
-   stream with no barrier in between, so the uploads of later chunks overlap the first passes of earlier ones and the
-   result copies of x and u are queued back to back.  (Descending stream priorities, to let early chunks finish and
-   download while later ones still compute, were measured and made things slightly slower; all chunks are equal.) */
+static int run_engine(ilqgb_handle *h, const io_t *io)
+{
+    int i, remaining, rc = 0;
+    const int prio = io && h->e2e_prio && h->n > 1;
+    struct timespec nap = {0, 20000};
+    if (fork_streams(h)) return -1;
+    if (prio) { /* the end-to-end solve runs on prioritised streams; they fork from the main stream like the others */
+        for (i = 0; i < h->n; i++) {
+            chunk *c = h->c[i];
+            if (ilqgk_set_device(c->device)) return hfail(h, NULL);
+            if (!c->stream_io && ilqgk_stream_create_prio(&c->stream_io, c->prio_rank, c->prio_n)) return hfail(h, NULL);
+            if (ilqgk_stream_wait_event(c->stream_io, h->ev_fork)) return hfail(h, NULL);
+            c->stream = c->stream_io;
+        }
+    }
+    for (i = 0; i < h->n; i++) {
+        chunk *c = h->c[i];
+        c->poll_issued = c->poll_seen = c->stop = c->phase = c->gate_recorded = 0;
+        if (io && ck_upload(c, io->x0 + (size_t)h->first[i] * h->d.nx, io->u_nom + (size_t)h->first[i] * h->T * h->d.nu)) { rc = hfail(h, c); goto out; }
+    }
+    remaining = h->n;
+    while (remaining > 0) {
+        int progressed = 0;
+        for (i = 0; i < h->n; i++) {
+            chunk *c = h->c[i];
+            const int max_iter = c->o.max_iter;
+            if (c->phase == 3) continue;
+            if (ilqgk_set_device(c->device)) { rc = hfail(h, NULL); goto out; }
+            if (c->phase == 0) { /* start, possibly gated on the previous chunk of the same device */
+                if (io && h->e2e_stagger > 0 && c->prio_rank > 0) {
+                    chunk *prev = h->c[i - 1];
+                    if (!prev->gate_recorded) continue;
+                    if (ilqgk_stream_wait_event(c->stream, prev->ev_gate)) { rc = hfail(h, NULL); goto out; }
+                }
+                if (ck_start(c)) { rc = hfail(h, c); goto out; }
+                c->phase = 1;
+                progressed = 1;
+            }
+            if (engine_poll(c)) { rc = hfail(h, c); goto out; }
+            if (c->phase == 1 && !c->stop && c->iter < max_iter && c->poll_issued - c->poll_seen < ENGINE_LOOKAHEAD) {
+                int n = max_iter - c->iter < ENGINE_BLOCK ? max_iter - c->iter : ENGINE_BLOCK;
+                while (n-- > 0) {
+                    if (launch_pass(c, 1, 1, 1)) { rc = hfail(h, c); goto out; }
+                    c->iter++;
+                    if (io && h->e2e_stagger > 0 && !c->gate_recorded && c->iter >= h->e2e_stagger) {
+                        if (ilqgk_event_record(c->ev_gate, c->stream)) { rc = hfail(h, NULL); goto out; }
+                        c->gate_recorded = 1;
+                    }
+                }
+                if (c->iter < max_iter) {
+                    const int slot = c->poll_issued % POLL_RING;
+                    if (ilqgk_launch_count_active(&c->w, c->d_counter, c->stream) || ilqgk_d2h(&c->h_poll[slot], c->d_counter, sizeof(int), c->stream) ||
+                        ilqgk_event_record(c->ev_poll[slot], c->stream)) { rc = hfail(h, NULL); goto out; }
+                    c->n_launches++;
+                    c->poll_issued++;
+                }
+                progressed = 1;
+            }
+            if (c->phase == 1 && (c->stop || c->iter >= max_iter)) { /* iteration limit bookkeeping (iLQG.c:365-377), results out */
+                if (!c->gate_recorded) {
+                    if (ilqgk_event_record(c->ev_gate, c->stream)) { rc = hfail(h, NULL); goto out; }
+                    c->gate_recorded = 1;
+                }
+                if (ilqgk_launch_finalize(&c->w, max_iter, c->stream)) { rc = hfail(h, NULL); goto out; }
+                c->n_launches++;
+                if (io) {
+                    const size_t f = (size_t)h->first[i];
+                    if (ck_download_async(c, io->x ? io->x + f * (h->T + 1) * h->d.nx : NULL, io->u ? io->u + f * h->T * h->d.nu : NULL,
+                                          io->cost ? io->cost + f : NULL, io->iterations ? io->iterations + f : NULL,
+                                          io->result ? io->result + f : NULL, io->n_linesearch ? io->n_linesearch + f : NULL)) { rc = hfail(h, c); goto out; }
+                }
+                c->phase = 3;
+                remaining--;
+                progressed = 1;
+            }
+        }
+        if (!progressed) nanosleep(&nap, NULL);
+    }
+out:
+    if (join_streams(h)) rc = -1;
+    if (prio) {
+        if (ilqgb_sync(h)) rc = -1;
+        for (i = 0; i < h->n; i++) h->c[i]->stream = h->c[i]->stream_main;
+    }
+    return rc;
+}
+
+int ilqgb_solve(ilqgb_handle *h) { return run_engine(h, NULL); }
+
+/* End to end from and to host buffers (pinned for full overlap); same results as upload + solve + download. */
 int ilqgb_solve_host(ilqgb_handle *h, const double *x0, const double *u_nom, double *x, double *u, double *cost,
                      int *iterations, int *result, int *n_linesearch)
 {
-    int i, pass;
-    const int max_iter = h->c[0]->o.max_iter;
-    if (ilqgk_set_device(h->device)) return hfail(h, NULL);
-    if (fork_streams(h)) return -1;
-    for (i = 0; i < h->n; i++) {
-        chunk *c = h->c[i];
-        if (ck_upload(c, x0 + (size_t)h->first[i] * h->d.nx, u_nom + (size_t)h->first[i] * h->T * h->d.nu)) return hfail(h, c);
-        if (ck_start(c)) return hfail(h, c);
-    }
-    for (pass = 0; pass < max_iter; pass++) {
-        for (i = 0; i < h->n; i++) {
-            if (launch_pass(h->c[i], 1, 1, 1)) return hfail(h, h->c[i]);
-            h->c[i]->iter++;
-        }
-        if ((pass + 1) % (4 * ACTIVE_CHECK_EVERY) == 0 && pass + 1 < max_iter && ilqgb_active(h) == 0) break;
-    }
-    for (i = 0; i < h->n; i++) {
-        chunk *c = h->c[i];
-        const size_t f = (size_t)h->first[i];
-        if (ilqgk_launch_finalize(&c->w, c->o.max_iter, c->stream)) return hfail(h, NULL);
-        if (ck_download_async(c, x ? x + f * (h->T + 1) * h->d.nx : NULL, u ? u + f * h->T * h->d.nu : NULL, cost ? cost + f : NULL,
-                              iterations ? iterations + f : NULL, result ? result + f : NULL, n_linesearch ? n_linesearch + f : NULL))
-            return hfail(h, c);
-    }
-    if (join_streams(h)) return -1;
+    io_t io = {x0, u_nom, x, u, cost, iterations, result, n_linesearch};
+    if (!x0 || !u_nom) { snprintf(h->err, sizeof h->err, "x0 and u_nom are required"); return -1; }
+    if (run_engine(h, &io)) return -1;
     return ilqgb_sync(h);
 }
 
 int ilqgb_sync(ilqgb_handle *h)
 {
     int i;
-    if (ilqgk_set_device(h->device)) return hfail(h, NULL);
     for (i = 0; i < h->n; i++)
         if (ck_sync(h->c[i])) return hfail(h, h->c[i]);
+    if (ilqgk_set_device(h->device)) return hfail(h, NULL);
     return ilqgk_stream_sync(h->stream) ? hfail(h, NULL) : 0;
 }
 

@@ -58,6 +58,9 @@ class Library:
         L.ilqgb_param_size.argtypes = [ci]
         L.ilqgb_create.restype = vp
         L.ilqgb_create.argtypes = [ci, ci, ci, ci, vp]
+        L.ilqgb_create_multi.restype = vp
+        L.ilqgb_create_multi.argtypes = [ci, vp, ci, ci, ci, vp]
+        L.ilqgb_devices.argtypes = [vp]
         L.ilqgb_destroy.argtypes = [vp]
         L.ilqgb_last_error.restype = cp
         L.ilqgb_last_error.argtypes = [vp]
@@ -101,13 +104,22 @@ class Library:
 
 
 class BatchSolver:
-    def __init__(self, problem, full_ddp=0, batch=1, n_hor=1, device=0, flags=0, stream=None, chunks=0):
+    def __init__(self, problem, full_ddp=0, batch=1, n_hor=1, device=0, flags=0, stream=None, chunks=0, devices=None):
+        """`devices`: list of GPU indices (or a count) to shard the batch over in this one process (ilqgb_create_multi);
+        `chunks` then counts chunks per device.  Default: the single GPU `device`."""
         self.L = Library(problem, full_ddp)
         self.lib = self.L.lib
         self.B, self.T = int(batch), int(n_hor)
         self.nx, self.nu = self.L.nx, self.L.nu
         self.max_iter = 20
-        self.h = self.lib.ilqgb_create(int(device), self.B, self.T, int(flags) | ((int(chunks) & 0xff) << 8), C.c_void_p(stream) if stream else None)
+        fl = int(flags) | ((int(chunks) & 0xff) << 8)
+        st = C.c_void_p(stream) if stream else None
+        if devices is None:
+            self.h = self.lib.ilqgb_create(int(device), self.B, self.T, fl, st)
+        else:
+            devs = list(range(devices)) if isinstance(devices, int) else [int(d) for d in devices]
+            arr = (C.c_int * len(devs))(*devs)
+            self.h = self.lib.ilqgb_create_multi(len(devs), arr, self.B, self.T, fl, st)
         if not self.h:
             raise RuntimeError("ilqgb_create failed: " + self.lib.ilqgb_last_error(None).decode())
 
@@ -241,6 +253,9 @@ class BatchSolver:
 
     def chunks(self):
         return int(self.lib.ilqgb_chunks(self.h))
+
+    def devices(self):
+        return int(self.lib.ilqgb_devices(self.h))
 
     def launch_count(self):
         return int(self.lib.ilqgb_launch_count(self.h))

@@ -105,3 +105,22 @@ def brachi_hli(n=500):
     u0 = -np.ones((n, 1))
     opts = {"max_iter": 20.0, "w_pen_init_l": 40.0, "w_pen_init_f": 1e-5, "w_pen_max_f": 1.0, "w_pen_fact2": 1.0}
     return params, x0, u0, opts
+
+
+# ---- twin-motor pendulum: running equality (hle) + terminal inequality (hfi) + torque limits (authored here) ------------
+PEND_PARAMS = {"dt": [0.02], "gl": [9.81], "cu": [0.01, 0.03], "cx": [0.1, 0.01], "cf": [5.0, 1.0], "lim": [-3.0, 3.0], "thmin": [0.5]}
+PEND_T = 200
+
+
+def pend_batch(B, T=PEND_T, seed=7, first=0):
+    """x0 = [U(1.5, 3), U(-1, 1)], u0 = 0.1*N(0,1) on both motors (unequal: the equality constraint starts violated)."""
+    b = np.arange(first, first + B, dtype=np.uint64)
+    x0 = np.zeros((B, 2))
+    x0[:, 0] = 1.5 + 1.5 * uniform01(seed, b, 0)
+    x0[:, 1] = -1.0 + 2.0 * uniform01(seed, b, 1)
+    idx = np.arange(T * 2, dtype=np.uint64)[None, :] + np.uint64(16)
+    u0 = 0.1 * normal(seed, b[:, None], idx).reshape(B, T, 2)
+    return x0, u0
+
+
+PEND_OPTS = {"max_iter": 60.0, "w_pen_fact2": 2.0}

@@ -6,6 +6,8 @@
  *
  * What each entry point replaces in the reference (file:line in jgeisler0303/DDP-Generator):
  *   ilqgb_create / ilqgb_destroy   allocation of trajectories/multipliers by the caller, iLQG_mex.c:100-103, 141-143
+ *   ilqgb_create_multi             the same for a batch sharded over several GPUs (no counterpart in the reference, which
+ *                                  solves one problem per call)
  *   ilqgb_standard_parameters      standard_parameters(), iLQG.c:57-78
  *   ilqgb_set_opt                  setOptParam(), iLQG.c:91-216 (same names, validation and messages)
  *   ilqgb_set_param                binding of the parameter struct by name, iLQG_mex.c:70-84 / paramdesc, iLQG.h:97-99
@@ -51,6 +53,13 @@ int ilqgb_deriv_doubles_per_step(void); /* time-varying derivative doubles the d
 
 /* lifecycle; `stream` may be NULL (the handle then owns a stream) or a cudaStream_t of the caller */
 ilqgb_handle *ilqgb_create(int device, int batch, int n_hor, int flags, void *stream);
+/* one handle over several GPUs of this process (SURVEY.md 8b "new batched entry ... n_gpus", 8e): the batch is cut into one
+ * contiguous shard per device, every call below fans out over all of them, host buffers are indexed by the global problem
+ * number, so ilqgb_download / ilqgb_solve_host gather the results of all devices into the caller's single arrays.  No
+ * collective and no peer access are involved.  devices = NULL means 0..n_devices-1; `stream` (optional) belongs to
+ * devices[0]; ILQGB_CHUNKS(n) counts chunks per device. */
+ilqgb_handle *ilqgb_create_multi(int n_devices, const int *devices, int batch, int n_hor, int flags, void *stream);
+int ilqgb_devices(const ilqgb_handle *h);
 void ilqgb_destroy(ilqgb_handle *h);
 const char *ilqgb_last_error(const ilqgb_handle *h); /* h may be NULL for creation errors */
 
@@ -72,8 +81,10 @@ int ilqgb_iterate(ilqgb_handle *h, int n_passes); /* returns passes actually lau
 int ilqgb_finish(ilqgb_handle *h);
 int ilqgb_solve(ilqgb_handle *h);
 int ilqgb_sync(ilqgb_handle *h);
-/* upload + solve + download in one call, pipelined across the handle's chunks (host buffers should be pinned); same
- * results as ilqgb_upload + ilqgb_solve + ilqgb_download.  Any output pointer may be NULL.  Synchronises. */
+/* upload + solve + download in one call (host buffers should be pinned); same results as ilqgb_upload + ilqgb_solve +
+ * ilqgb_download.  Chunks run on streams of descending priority, so they finish one after the other and the result copies
+ * of one chunk overlap the passes of the next ones (ILQG_E2E_PRIO=0 in the environment turns that off).  Any output pointer
+ * may be NULL.  Synchronises. */
 int ilqgb_solve_host(ilqgb_handle *h, const double *x0, const double *u_nom, double *x, double *u, double *cost,
                      int *iterations, int *result, int *n_linesearch);
 int ilqgb_active(ilqgb_handle *h); /* problems still running (synchronises) */

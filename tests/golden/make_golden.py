@@ -103,6 +103,18 @@ def kats():
     return out
 
 
+def make_pend():
+    """Running equality (hle) + terminal inequality (hfi): four problems per FULL_DDP setting, incl. one that fails."""
+    xp, up = W.pend_batch(4)
+    for ddp in (0, 1):
+        for b in range(4):
+            fx = solve_fixture("pend", ddp, W.PEND_T, W.PEND_PARAMS, xp[b], up[b], W.PEND_OPTS, with_qp=True)
+            s = oracle_lib.OracleLib("reference", "pend", ddp).solver(W.PEND_T)
+            s.set_opts(W.PEND_OPTS); s.set_params(W.PEND_PARAMS); s.init(xp[b], up[b]); s.solve()
+            fx["mult_t"] = s.get("mult_t")
+            np.savez_compressed(os.path.join(HERE, f"pend_b{b}_ddp{ddp}.npz"), **fx)
+
+
 def main():
     assert oracle_lib.available("reference", "car", 0), "build oracle/_ref first (make -C oracle ref)"
     x0, u0 = W.car_single()
@@ -134,6 +146,7 @@ def main():
         s.set_opts(opts); s.set_params(params); s.init(bx0, bu0); s.solve()
         fx["mult_t"] = s.get("mult_t")
         np.savez_compressed(os.path.join(HERE, f"brachi_hli_ddp{ddp}.npz"), **fx)
+    make_pend()
     np.savez_compressed(os.path.join(HERE, "kats.npz"), **kats())
     # bit patterns of the deterministic math layer on a fixed grid
     lib = C.CDLL(os.path.join(ROOT, "oracle", "_build", "libdmcheck.so"))
@@ -148,4 +161,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "pend":      # only the fixtures added in round 2 (the others stay byte-identical)
+        make_pend()
+    else:
+        main()

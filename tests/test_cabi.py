@@ -10,7 +10,7 @@ import ilqg_b200
 import oracle_lib
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIBS = [("car", 0), ("car", 1), ("brachi", 0), ("brachi", 1), ("quad", 0), ("quad", 1), ("carhx", 0), ("brachi_hli", 1)]
+LIBS = [("car", 0), ("car", 1), ("brachi", 0), ("brachi", 1), ("quad", 0), ("quad", 1), ("carhx", 0), ("brachi_hli", 1), ("pend", 0), ("pend", 1)]
 
 
 def declared_symbols():

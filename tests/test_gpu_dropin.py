@@ -56,6 +56,13 @@ def test_brachi_hli_through_reference_api():
     compare("brachi_hli", 0, 500, params, x0, u0, opts)
 
 
+@pytest.mark.parametrize("b,ddp", [(0, 0), (1, 1), (3, 1)])
+def test_pend_through_reference_api(b, ddp):
+    """running equality + terminal inequality multipliers through the tOptSet marshalling (b=1/ddp=1 is a failed solve)"""
+    x0, u0 = W.pend_batch(4)
+    compare("pend", ddp, W.PEND_T, W.PEND_PARAMS, x0[b], u0[b], W.PEND_OPTS)
+
+
 def test_carhx_through_reference_api():
     x0, u0 = W.car_single()
     compare("carhx", 0, 500, W.CARHX_PARAMS, x0, u0, {"max_iter": 40})

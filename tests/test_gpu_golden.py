@@ -62,6 +62,29 @@ def test_brachi_running_inequality_golden(ddp):
 
 
 @pytest.mark.parametrize("ddp", [0, 1])
+def test_pendulum_running_equality_and_terminal_inequality_golden(ddp):
+    """hle running equality + hfi terminal inequality + torque limits, four problems as one batch (one of them fails for
+    FULL_DDP=1): solver record, box-QP active sets, running multipliers mu_le[k] / last_hle[k] and final mu_fi / last_hfi."""
+    import ilqg_b200
+    gs = [np.load(os.path.join(GOLD, f"pend_b{b}_ddp{ddp}.npz")) for b in range(4)]
+    x0, u0 = np.stack([g["x0"] for g in gs]), np.stack([g["u0"] for g in gs])
+    recs = PU.gpu_records("pend", ddp, W.PEND_T, W.PEND_PARAMS, x0, u0, W.PEND_OPTS)
+    for b, g in enumerate(gs):
+        PU.assert_same(recs[b], {k: g[k] for k in KEYS}, f"pend_b{b}_ddp{ddp}", keys=KEYS)
+        if (g["qp_ret_last"] >= 1).all():
+            code = recs[b]["tr_clamp"]
+            assert np.array_equal(np.stack([code & 3, (code >> 2) & 3], axis=1)[::-1], g["qp_clamped_last"])
+    s = ilqg_b200.BatchSolver("pend", ddp, 4, W.PEND_T)
+    s.set_options(W.PEND_OPTS); s.set_params(W.PEND_PARAMS); s.solve(x0, u0)
+    mu_f, last_f, mu_r, last_r = s.get("mu_f"), s.get("last_f"), s.get("mu_r"), s.get("last_r")
+    for b, g in enumerate(gs):
+        assert mu_f[b].ravel()[0] == g["mult_f"][0] and last_f[b].ravel()[0] == g["mult_f"][1], b      # mu_fi, last_hfi
+        assert np.array_equal(mu_r[b].reshape(W.PEND_T), g["mult_t"][:, 0]), b                          # mu_le[k]
+        assert np.array_equal(last_r[b].reshape(W.PEND_T), g["mult_t"][:, 1]), b                        # last_hle[k]
+    s.close()
+
+
+@pytest.mark.parametrize("ddp", [0, 1])
 def test_quad_golden(ddp):
     gs = [np.load(os.path.join(GOLD, f"quad_T300_b{b}_ddp{ddp}.npz")) for b in range(2)]
     recs = PU.gpu_records("quad", ddp, 300, W.QUAD_PARAMS, np.stack([g["x0"] for g in gs]), np.stack([g["u0"] for g in gs]), {"max_iter": 25})

@@ -74,6 +74,24 @@ def test_brachistochrone_running_inequality(ddp):
     assert (g["x"][:, 0] - params["ymin"]).min() > -1e-5      # the path respects the running bound y >= ymin[k]
 
 
+@pytest.mark.parametrize("b", range(4))
+@pytest.mark.parametrize("ddp", [0, 1])
+def test_pendulum_running_equality_and_terminal_inequality(b, ddp):
+    """hle (running equality, iLQG_func.tem:427-453) and hfi (terminal inequality, iLQG_func.tem:470-509): the two constraint
+    kinds no reference example uses.  Fixture b=1/ddp=1 is a failed solve (result 0)."""
+    check_solve(f"pend_b{b}_ddp{ddp}.npz", "pend", ddp, W.PEND_T, W.PEND_PARAMS, W.PEND_OPTS, with_qp=True)
+    g = np.load(os.path.join(GOLD, f"pend_b{b}_ddp{ddp}.npz"))
+    for kind in kinds("pend", ddp):
+        s = oracle_lib.OracleLib(kind, "pend", ddp).solver(W.PEND_T)
+        s.set_opts(W.PEND_OPTS); s.set_params(W.PEND_PARAMS); s.init(g["x0"], g["u0"]); s.solve()
+        assert np.array_equal(s.get("mult_t"), g["mult_t"]), kind      # mu_le[k], last_hle[k]
+        s.close()
+    if int(g["result"]) == 1:       # the fixture itself: both constraints are active and satisfied at the solution
+        assert np.abs(g["u"][:, 0] - g["u"][:, 1]).max() < 1e-6
+        assert abs(g["x"][-1, 0] - W.PEND_PARAMS["thmin"][0]) < 1e-3 and g["mult_f"][0] > 1.0
+        assert np.abs(g["mult_t"][:, 0]).max() > 1e-3
+
+
 def test_brachistochrone_reaches_cycloid_time():
     """Sanity of the fixture itself: n=500 converges towards the analytic cycloid time pi*sqrt(2/g)."""
     g = np.load(os.path.join(GOLD, "brachi_n500_ddp0.npz"))
