@@ -163,10 +163,20 @@ int ilqgk_launch_ls_tail(const ilqg_work *w, const ilqg_opts *o, const double *p
 {
     const int nrem = o->n_alpha - from;
     const ParamBlock<P> pb = make_pb(params);
+    const bool par = o->ls_commit_par && w->ls_ckpt;
     if (from == 0 && check(cudaMemsetAsync(w->ls_mask, 0, sizeof(int) * w->Bp, (cudaStream_t)stream), "memset ls_mask")) return -1;
-    PP_DISPATCH(w, (k_ls_tail<P, PP><<<nblk(w->B * nrem, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, pb, from)));
+    if (par)
+        PP_DISPATCH(w, (k_ls_tail<P, PP, true><<<nblk(w->B * nrem, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, pb, from)));
+    else
+        PP_DISPATCH(w, (k_ls_tail<P, PP, false><<<nblk(w->B * nrem, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, pb, from)));
     if (check(cudaGetLastError(), "k_ls_tail")) return -1;
-    PP_DISPATCH(w, (k_ls_commit<P, PP><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, pb, iter, from)));
+    if (par) {
+        dim3 grid(nblk(w->B, BP_BLOCK), LS_SEGS);
+        PP_DISPATCH(w, (k_ls_commit_seg<P, PP><<<grid, BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, pb, from)));
+        if (check(cudaGetLastError(), "k_ls_commit_seg")) return -1;
+        PP_DISPATCH(w, (k_ls_commit<P, PP, true><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, pb, iter, from)));
+    } else
+        PP_DISPATCH(w, (k_ls_commit<P, PP, false><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, pb, iter, from)));
     return check(cudaGetLastError(), "k_ls_commit");
 }
 
@@ -175,6 +185,28 @@ int ilqgk_launch_post(const ilqg_work *w, const ilqg_opts *o, const double *para
     if (P::N_MU_R + P::N_MU_F == 0) return 0;   /* cost does not depend on multipliers/penalties: nothing to redo */
     PP_DISPATCH(w, (k_post<P, PP><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, make_pb(params))));
     return check(cudaGetLastError(), "k_post");
+}
+
+int ilqgk_launch_mult(const ilqg_work *w, const ilqg_opts *o, const double *params, int init, void *stream)
+{
+    if (P::N_MU_R + P::N_MU_F == 0) return 0;
+    PP_DISPATCH(w, (k_mult<P, PP><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, *o, make_pb(params), init)));
+    return check(cudaGetLastError(), "k_mult");
+}
+
+int ilqgk_dense_size(void) { return P::DENSE_SIZE; }
+
+int ilqgk_launch_dense(const ilqg_work *w, const double *params, double *out, void *stream)
+{
+    dim3 grid(nblk(w->B, DV_BLOCK), (unsigned)w->T);
+    PP_DISPATCH(w, (k_dense<P, PP><<<grid, DV_BLOCK, 0, (cudaStream_t)stream>>>(*w, make_pb(params), out)));
+    return check(cudaGetLastError(), "k_dense");
+}
+
+int ilqgk_launch_clamp(const ilqg_work *w, const double *params, double *xu_io, int k, void *stream)
+{
+    PP_DISPATCH(w, (k_clamp<P, PP><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, make_pb(params), xu_io, k)));
+    return check(cudaGetLastError(), "k_clamp");
 }
 
 int ilqgk_has_post(void) { return (P::N_MU_R + P::N_MU_F) > 0; }

@@ -51,6 +51,10 @@ int ilqgk_launch_ls_reset(const ilqg_work *w, void *stream);
 int ilqgk_launch_ls_round(const ilqg_work *w, const ilqg_opts *o, const double *params, int iter, int round, void *stream);
 int ilqgk_launch_ls_tail(const ilqg_work *w, const ilqg_opts *o, const double *params, int iter, int from, void *stream);
 int ilqgk_launch_post(const ilqg_work *w, const ilqg_opts *o, const double *params, void *stream);
+int ilqgk_launch_mult(const ilqg_work *w, const ilqg_opts *o, const double *params, int init, void *stream);
+int ilqgk_dense_size(void);
+int ilqgk_launch_dense(const ilqg_work *w, const double *params, double *out /* [B][T][dense_size] */, void *stream);
+int ilqgk_launch_clamp(const ilqg_work *w, const double *params, double *xu_io /* [B][nx+nu] */, int k, void *stream);
 int ilqgk_has_post(void);
 int ilqgk_launch_finalize(const ilqg_work *w, int max_iter, void *stream);
 int ilqgk_launch_count_active(const ilqg_work *w, int *d_counter, void *stream);

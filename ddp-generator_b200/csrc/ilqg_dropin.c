@@ -3,7 +3,8 @@
  * A caller written against the reference's API (the mex gateway iLQG_mex.c:59-137 is the only shipped one) calls
  *     standard_parameters, setOptParam, init_opt, forward_pass(candidates[0], o, 0.0, &cost, 0),
  *     makeCandidateNominal, iLQG
- * on a caller-allocated tOptSet.  This file exports exactly those symbols (plus the paramdesc globals the binding
+ * on a caller-allocated tOptSet.  This file exports those symbols and the solver's public phases (calc_derivs, back_pass,
+ * line_search, update_multipliers, clampU: iLQG.h:83-86, back_pass.h:7, line_search.h:6) (plus the paramdesc globals the binding
  * reads, iLQG.h:97-99) on top of the batched C ABI with a batch of one: state is marshalled between the caller's
  * array-of-structs trajectories and the device layout, every rollout / derivative / backward pass / line search
  * runs in the CUDA kernels.  Compiled per problem against the generated iLQG_problem.h, like the reference.
@@ -109,7 +110,16 @@ void makeCandidateNominal(tOptSet *o, int idx)
     o->candidates[idx] = t;
 }
 
-void printParams(double **p, int k) { (void)p; (void)k; }
+void printParams(double **p, int k)
+{
+    int i, j;
+    for (i = 0; i < n_params; i++) {
+        const int n = paramdesc[i]->size == -1 ? 1 : paramdesc[i]->size;
+        PRNT("%s= ", paramdesc[i]->name);
+        for (j = 0; j < n; j++) PRNT("%g ", paramdesc[i]->size == -1 ? p[i][k] : p[i][j]);
+        PRNT("\n");
+    }
+}
 int get_g_size() { return 0; }
 int calcG(double g[], trajEl_t *t, int k, double *p[]) { (void)g; (void)t; (void)k; (void)p; return 1; }
 
@@ -254,6 +264,160 @@ static int pull_traj(ilqgb_handle *h, traj_t *dst, const char *fx, const char *f
     if (!rc) memcpy(dst->f.x, x + (size_t)T * N_X, sizeof dst->f.x);
     free(x);
     return rc ? -1 : 0;
+}
+
+
+/* ---- the solver's phases on their own (iLQG.h:83,86; back_pass.h:7; line_search.h:6; iLQG_func.tem:68) --------------------------
+ * Each call is self-contained: the caller's tOptSet is marshalled to the device, the phase runs in its kernel, and exactly the
+ * members the reference's function writes are copied back.  The derivative members of trajEl_t are filled by calc_derivs for
+ * inspection (fx fu cx cxx cu cuu cxu, limits and their gradients; the FULL_DDP tensors fxx/fuu/fxu stay on the device), but
+ * back_pass does not read them from the host struct: it re-evaluates them on the device from the nominal x, u -- the same bits. */
+static int push_all(ilqgb_handle *h, tOptSet *o, int with_law)
+{
+    int one = 1, zero = 0, rc = 0;
+    if (push_options(h, o) || push_params(h, o) || push_state(h, o, with_law)) return -1;
+    rc |= ilqgb_put(h, "lambda", &o->lambda) < 0;
+    rc |= ilqgb_put(h, "dV0", &o->dV[0]) < 0;
+    rc |= ilqgb_put(h, "dV1", &o->dV[1]) < 0;
+    rc |= ilqgb_put(h, "g_norm", &o->g_norm) < 0;
+    rc |= ilqgb_put(h, "new_cost", &o->new_cost) < 0;
+    rc |= ilqgb_put(h, "dcost", &o->dcost) < 0;
+    rc |= ilqgb_put(h, "expected", &o->expected) < 0;
+    rc |= ilqgb_put_int(h, "new_deriv", &one) < 0;
+    rc |= ilqgb_put_int(h, "deriv_fail", &zero) < 0;
+    rc |= ilqgb_put_int(h, "bp_done", &zero) < 0;
+    rc |= ilqgb_set_tuning(h, "pass_index", 0) < 0;
+    if (o->max_iter > g_trace_len) g_trace_len = o->max_iter;
+    return rc ? -1 : 0;
+}
+
+int calc_derivs(tOptSet *o)
+{
+    ilqgb_handle *h = handle_for(o->n_hor);
+    const int T = o->n_hor, DS = ilqgb_dense_size();
+    int fail = 0, k;
+    double *buf, *fd;
+    if (!h || push_all(h, o, 0) || ilqgb_phase_derivs(h)) return 0;
+    if (ilqgb_get_int(h, "deriv_fail", &fail) < 0 || fail) return 0;
+    buf = (double *)malloc(sizeof(double) * ((size_t)T * DS + N_X + sizeofQxx));
+    if (!buf) return 0;
+    fd = buf + (size_t)T * DS;
+    if (ilqgb_get(h, "dense", buf) < 0 || ilqgb_get(h, "fd", fd) < 0) { free(buf); return 0; }
+    for (k = 0; k < T; k++) {
+        trajEl_t *t = &o->nominal->t[k];
+        const double *d = buf + (size_t)k * DS;
+#define TAKE(member) do { memcpy(t->member, d, sizeof t->member); d += sizeof t->member / sizeof(double); } while (0)
+        TAKE(fx); TAKE(fu); TAKE(cx); TAKE(cxx); TAKE(cu); TAKE(cuu); TAKE(cxu);
+        TAKE(lower); TAKE(upper); TAKE(lower_sign); TAKE(upper_sign); TAKE(lower_hx); TAKE(upper_hx);
+#undef TAKE
+    }
+    memcpy(o->nominal->f.cx, fd, sizeof o->nominal->f.cx);
+    memcpy(o->nominal->f.cxx, fd + N_X, sizeof o->nominal->f.cxx);
+    free(buf);
+    return 1;
+}
+
+static void pull_law(ilqgb_handle *h, tOptSet *o)
+{
+    const int T = o->n_hor;
+    int k;
+    double *l = (double *)malloc(sizeof(double) * (size_t)T * (N_U + N_U * N_X)), *L;
+    if (!l) return;
+    L = l + (size_t)T * N_U;
+    ilqgb_get(h, "l", l);
+    ilqgb_get(h, "L", L);
+    for (k = 0; k < T; k++) {
+        memcpy(o->nominal->t[k].l, l + (size_t)k * N_U, sizeof o->nominal->t[k].l);
+        memcpy(o->nominal->t[k].L, L + (size_t)k * N_U * N_X, sizeof o->nominal->t[k].L);
+    }
+    free(l);
+}
+
+/* returns 0 = ok, 1 = the box QP of some step failed (back_pass.c:163-171); o->lambda is the caller's business */
+int back_pass(tOptSet *o)
+{
+    ilqgb_handle *h = handle_for(o->n_hor);
+    int done = 0;
+    if (!h || push_all(h, o, 1) || ilqgb_phase_derivs(h) || ilqgb_phase_backpass_once(h)) return 1;
+    if (ilqgb_get_int(h, "bp_done", &done) < 0) return 1;
+    pull_law(h, o);                       /* a failed pass leaves the steps it reached rewritten, like the reference */
+    ilqgb_get(h, "dV0", &o->dV[0]);
+    ilqgb_get(h, "dV1", &o->dV[1]);
+    if (done) ilqgb_get(h, "g_norm", &o->g_norm);
+    return done ? 0 : 1;
+}
+
+int line_search(tOptSet *o, int iter)
+{
+    ilqgb_handle *h = handle_for(o->n_hor);
+    int cur = 0, rc;
+    if (!h || push_all(h, o, 1)) return 0;
+    /* every alpha as its own stored rollout, so that candidates[0] holds the last rollout tried, accepted or not */
+    if (ilqgb_set_tuning(h, "ls_tail_from", o->n_alpha)) return 0;
+    rc = ilqgb_phase_linesearch(h);
+    ilqgb_set_tuning(h, "ls_tail_from", -1);
+    if (rc || ilqgb_get_int(h, "cur", &cur) < 0) return 0;
+    ilqgb_get(h, "new_cost", &o->new_cost);
+    ilqgb_get(h, "dcost", &o->dcost);
+    ilqgb_get(h, "expected", &o->expected);
+    {   /* the phase ran as pass 0: row 0 of the traces is this call's log entry */
+        int *a = (int *)malloc(sizeof(int) * g_trace_len);
+        double *z = (double *)malloc(sizeof(double) * 2 * g_trace_len), *c = z ? z + g_trace_len : NULL;
+        if (a && z && ilqgb_get_int(h, "tr_alpha", a) > 0 && ilqgb_get(h, "tr_z", z) > 0 && ilqgb_get(h, "tr_newcost", c) > 0) {
+            if (o->log_linesearch) o->log_linesearch[iter] = a[0];
+            if (o->log_z) o->log_z[iter] = z[0];
+            if (o->log_cost) o->log_cost[iter] = c[0];
+        }
+        free(a);
+        free(z);
+    }
+    /* the device has already flipped its buffers for an accepted step; here that stays with the caller (iLQG.c:322) */
+    if (pull_traj(h, o->candidates[0], cur ? "x" : "x_cand", cur ? "u" : "u_cand", o->n_hor)) return 0;
+    return cur ? 1 : 0;
+}
+
+int update_multipliers(tOptSet *o, int init)
+{
+    ilqgb_handle *h = handle_for(o->n_hor);
+    const int T = o->n_hor, n_r = N_EL / 2, n_f = N_FIN / 2;
+    int n_le = 0, n_fe = 0, i, k;
+    double *mr, *lr, *mf, *lf;
+    if (n_r + n_f == 0) return 1;
+    if (!h || push_all(h, o, 0) || ilqgb_phase_multipliers(h, init)) return 0;
+    ilqgb_mult_counts(&n_le, &n_fe);
+    mr = (double *)malloc(sizeof(double) * (2 * (size_t)T * (n_r + 1) + 2 * (n_f + 1)));
+    if (!mr) return 0;
+    lr = mr + (size_t)T * (n_r + 1); mf = lr + (size_t)T * (n_r + 1); lf = mf + n_f + 1;
+    if (n_r) { ilqgb_get(h, "mu_r", mr); ilqgb_get(h, "last_r", lr); }
+    if (n_f) { ilqgb_get(h, "mu_f", mf); ilqgb_get(h, "last_f", lf); }
+    for (k = 0; k < T; k++)
+        for (i = 0; i < n_r; i++) {
+            int a, b;
+            mult_layout(n_r, n_le, i, &a, &b);
+            ((double *)&o->multipliers.t[k])[a] = mr[(size_t)k * n_r + i];
+            ((double *)&o->multipliers.t[k])[b] = lr[(size_t)k * n_r + i];
+        }
+    for (i = 0; i < n_f; i++) {
+        int a, b;
+        mult_layout(n_f, n_fe, i, &a, &b);
+        ((double *)&o->multipliers.f)[a] = mf[i];
+        ((double *)&o->multipliers.f)[b] = lf[i];
+    }
+    free(mr);
+    ilqgb_get(h, "w_pen_l", &o->w_pen_l);
+    ilqgb_get(h, "w_pen_f", &o->w_pen_f);
+    return 1;
+}
+
+/* clampU has no tOptSet: the horizon comes from N, the parameters from p */
+void clampU(double *u, trajEl_t *t, int k, double **p, int N)
+{
+    ilqgb_handle *h = handle_for(N);
+    int i;
+    if (!h) return;
+    for (i = 0; i < n_params; i++)
+        if (ilqgb_set_param(h, i, p[i], paramdesc[i]->size == -1 ? N + 1 : paramdesc[i]->size)) return;
+    ilqgb_clamp_u(h, k, t->x, u);
 }
 
 /* ---- forward_pass (iLQG.h:82; iLQG_func.tem:121-185) --------------------------------------------------------------------------- */

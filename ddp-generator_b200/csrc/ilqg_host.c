@@ -78,6 +78,12 @@ static int fail(chunk *h, const char *msg)
 
 static int failk(chunk *h) { return fail(h, ilqgk_last_error()); }
 
+static int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
 static void *dalloc(chunk *h, size_t bytes)
 {
     void *p = NULL;
@@ -431,6 +437,7 @@ static chunk *ck_create(int device, int batch, int n_hor, int flags, void *strea
         DALLOC(w->ls_count, int, ILQG_MAX_ALPHA + 2);
         DALLOC(w->ls_cnew, double, (size_t)ILQG_MAX_ALPHA * Bp);
         DALLOC(w->ls_mask, int, Bp);
+        if (env_int("ILQG_LS_COMMIT_PAR", 1)) DALLOC(w->ls_ckpt, double, (size_t)ILQG_MAX_ALPHA * 32 * Bp * d->nx);
         DALLOC(w->n_dv, int, Bp);
         DALLOC(w->n_roll, int, Bp);
         DALLOC(w->n_tail, int, Bp);
@@ -709,6 +716,7 @@ static int launch_pass(chunk *h, int do_derivs, int do_back, int do_ls)
                                             : (h->total_B <= 17000 ? 0 : (h->total_B <= 24000 ? 1 : (h->total_B <= 50000 ? 2 : (h->total_B <= 140000 ? 3 : 4))));
             if (from > h->o.n_alpha || h->o.n_alpha - from < 2) from = h->o.n_alpha;
             h->o.ls_tail_from = from;
+            h->o.ls_commit_par = h->w.ls_ckpt != NULL;
             for (r = 0; r < from; r++) {
                 p = timing_begin(h, TC_LINESEARCH);
                 if (ilqgk_launch_ls_round(&h->w, &h->o, h->params, h->iter, r, h->stream)) return failk(h);
@@ -718,7 +726,7 @@ static int launch_pass(chunk *h, int do_derivs, int do_back, int do_ls)
             if (from < h->o.n_alpha) {
                 p = timing_begin(h, TC_LINESEARCH);
                 if (ilqgk_launch_ls_tail(&h->w, &h->o, h->params, h->iter, from, h->stream)) return failk(h);
-                h->n_launches += 2;
+                h->n_launches += h->o.ls_commit_par ? 3 : 2;
                 timing_end(h, p);
             }
         }
@@ -756,6 +764,48 @@ static int ck_sync(chunk *h)
 {
     if (ilqgk_set_device(h->device)) return failk(h);
     return ilqgk_stream_sync(h->stream) ? failk(h) : 0;
+}
+
+static int ck_phase_backpass_once(chunk *h)
+{
+    int rc;
+    if (ilqgk_set_device(h->device)) return failk(h);
+    h->o.bp_single = 1;
+    rc = launch_pass(h, 0, 1, 0);
+    h->o.bp_single = 0;
+    return rc;
+}
+
+static int ck_phase_multipliers(chunk *h, int init)
+{
+    if (ilqgk_set_device(h->device)) return failk(h);
+    if (ilqgk_launch_mult(&h->w, &h->o, h->params, init, h->stream)) return failk(h);
+    h->n_launches++;
+    return 0;
+}
+
+static int ck_clamp_u(chunk *h, int k, const double *x, double *u)
+{
+    const size_t B = (size_t)h->B, nx = (size_t)h->d.nx, nu = (size_t)h->d.nu;
+    size_t b;
+    double *tmp;
+    if (ilqgk_set_device(h->device)) return failk(h);
+    if (ensure_stage(h, B * (nx + nu))) return -1;
+    tmp = (double *)malloc(sizeof(double) * B * (nx + nu));
+    if (!tmp) return fail(h, "out of host memory");
+    for (b = 0; b < B; b++) {
+        memcpy(tmp + b * (nx + nu), x + b * nx, sizeof(double) * nx);
+        memcpy(tmp + b * (nx + nu) + nx, u + b * nu, sizeof(double) * nu);
+    }
+    if (ilqgk_h2d(h->d_stage, tmp, sizeof(double) * B * (nx + nu), h->stream) || ilqgk_launch_clamp(&h->w, h->params, h->d_stage, k, h->stream) ||
+        ilqgk_d2h(tmp, h->d_stage, sizeof(double) * B * (nx + nu), h->stream) || ilqgk_stream_sync(h->stream)) {
+        free(tmp);
+        return failk(h);
+    }
+    h->n_launches++;
+    for (b = 0; b < B; b++) memcpy(u + b * nu, tmp + b * (nx + nu) + nx, sizeof(double) * nu);
+    free(tmp);
+    return 0;
 }
 
 static int ck_phase_derivs(chunk *h) { return ilqgk_set_device(h->device) ? failk(h) : launch_pass(h, 1, 0, 0); }
@@ -814,6 +864,15 @@ static long ck_get(chunk *h, const char *f, double *out)
     const size_t B = (size_t)h->B;
     field_t fd;
     if (ilqgk_set_device(h->device)) return failk(h);
+    if (!strcmp(f, "dense")) { /* computed field: the dense per-step derivative record, rebuilt on the device */
+        const size_t n = B * (size_t)h->T * (size_t)ilqgk_dense_size();
+        if (ensure_stage(h, n)) return -1;
+        if (ilqgk_launch_dense(&h->w, h->params, h->d_stage, h->stream) || ilqgk_d2h(out, h->d_stage, sizeof(double) * n, h->stream) ||
+            ilqgk_stream_sync(h->stream))
+            return failk(h);
+        h->n_launches++;
+        return (long)n;
+    }
     if (find_field(h, f, &fd)) return -1;
     if (fd.scal) {
         if (ilqgk_d2h(out, fd.scal, sizeof(double) * B, h->stream) || ilqgk_stream_sync(h->stream)) return failk(h);
@@ -862,6 +921,8 @@ static long ck_get_int(chunk *h, const char *f, int *out)
     else if (!strcmp(f, "n_derivs")) scal = w->n_dv;
     else if (!strcmp(f, "n_rollouts")) scal = w->n_roll;
     else if (!strcmp(f, "n_tails")) scal = w->n_tail;
+    else if (!strcmp(f, "bp_done")) scal = w->bp_done;
+    else if (!strcmp(f, "deriv_fail")) scal = w->deriv_fail;
     if (scal) {
         if (ilqgk_d2h(out, scal, sizeof(int) * B, h->stream) || ilqgk_stream_sync(h->stream)) return failk(h);
         return (long)B;
@@ -893,6 +954,9 @@ static long ck_put_int(chunk *h, const char *f, const int *in)
     if (ilqgk_set_device(h->device)) return failk(h);
     if (!strcmp(f, "cur")) dst = h->w.cur;
     else if (!strcmp(f, "status")) dst = h->w.status;
+    else if (!strcmp(f, "new_deriv")) dst = h->w.new_deriv;
+    else if (!strcmp(f, "deriv_fail")) dst = h->w.deriv_fail;
+    else if (!strcmp(f, "bp_done")) dst = h->w.bp_done;
     else return fail(h, "unknown field");
     if (ilqgk_h2d(dst, in, sizeof(int) * B, h->stream) || ilqgk_stream_sync(h->stream)) return failk(h);
     return (long)B;
@@ -947,12 +1011,13 @@ struct ilqgb_handle {
 
 static int auto_chunks(int batch)
 {
-    /* measured on B200 (bench.py --batch B --chunks n, car): chunks of about 65 536 problems, at least two once there are
-       65 536, at most four (262 144: 6, 8, 12 chunks are slower for a resident solve).  Smaller batches still get two chunks
-       from 16 384 problems on, so that an end-to-end solve has something to overlap its copies with. */
-    int n = batch / 65536;
+    /* measured on B200 (scripts/gpu_probe_e2e.py, car, 20 passes): chunks of about 32 768 problems, at most eight, and two
+       from 16 384 problems on.  Resident solves are insensitive to the count (262 144 problems: 4 chunks 8.24 M it/s, 6: 8.11 M,
+       8: 8.12 M; 32 768: 1 chunk 5.39 M, 2: 5.47-5.56 M, 4: 5.43-5.53 M, 8: 5.02 M); end to end more, smaller chunks
+       shorten the exposed first upload and last download (262 144: 4 chunks 7.33 M, 8: 7.50 M; 32 768: 1 chunk 4.62 M, 2: 4.93 M). */
+    int n = batch / 32768;
     if (n < 2) n = batch >= 16384 ? 2 : 1;
-    if (n > 4) n = 4;
+    if (n > 8) n = 8;
     return n;
 }
 
@@ -990,12 +1055,6 @@ static int join_streams(ilqgb_handle *h)
 }
 
 const char *ilqgb_last_error(const ilqgb_handle *h) { return h ? h->err : g_create_err; }
-
-static int env_int(const char *name, int dflt)
-{
-    const char *v = getenv(name);
-    return v && *v ? atoi(v) : dflt;
-}
 
 ilqgb_handle *ilqgb_create_multi(int n_devices, const int *devices, int batch, int n_hor, int flags, void *stream)
 {
@@ -1356,6 +1415,42 @@ int ilqgb_sync(ilqgb_handle *h)
 FANOUT_PHASE(derivs)
 FANOUT_PHASE(backpass)
 FANOUT_PHASE(linesearch)
+FANOUT_PHASE(backpass_once)
+
+int ilqgb_phase_multipliers(ilqgb_handle *h, int init)
+{
+    int i;
+    if (fork_streams(h)) return -1;
+    for (i = 0; i < h->n; i++)
+        if (ck_phase_multipliers(h->c[i], init)) return hfail(h, h->c[i]);
+    return join_streams(h);
+}
+
+int ilqgb_clamp_u(ilqgb_handle *h, int k, const double *x, double *u)
+{
+    int i;
+    if (ilqgb_sync(h)) return -1;
+    for (i = 0; i < h->n; i++)
+        if (ck_clamp_u(h->c[i], k, x + (size_t)h->first[i] * h->d.nx, u + (size_t)h->first[i] * h->d.nu)) return hfail(h, h->c[i]);
+    return 0;
+}
+
+int ilqgb_dense_size(void) { return ilqgk_dense_size(); }
+
+/* run-time tuning knobs (the defaults are chosen from the batch size): "ls_tail_from" (sequential line-search rounds before the
+   parallel-alpha tail, >= n_alpha = all sequential), "bp_latency" (0/1: register-unconstrained back-pass build), and
+   "pass_index" (the loop index `iter` the next single phase runs as: row of the traces) */
+int ilqgb_set_tuning(ilqgb_handle *h, const char *name, int value)
+{
+    int i;
+    for (i = 0; i < h->n; i++) {
+        if (!strcmp(name, "ls_tail_from")) h->c[i]->ls_tail_from = value;
+        else if (!strcmp(name, "pass_index")) { h->c[i]->iter = value; h->c[i]->started = 1; }
+        else if (!strcmp(name, "bp_latency")) h->c[i]->bp_latency = value;
+        else { snprintf(h->err, sizeof h->err, "unknown tuning knob"); return -1; }
+    }
+    return 0;
+}
 
 long ilqgb_get(ilqgb_handle *h, const char *field, double *out)
 {

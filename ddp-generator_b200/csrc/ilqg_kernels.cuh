@@ -651,6 +651,11 @@ __global__ void __launch_bounds__(BP_BLOCK, MINB) k_backpass(Work w, Opts o, Par
                 w.tr_clamp[(size_t)k * Bp + b] = code;
             }
             if (qp < 1) {
+                /* the reference's boxQP iterates on t->l in place (back_pass.c:163-171): a failed QP leaves its last iterate
+                   in the trajectory, which is what a solve that ends on this failure returns */
+                double *rec = w.LL[cur] + ((size_t)k * Bp + b) * Rec<P>::RLL;
+#pragma unroll
+                for (int i = 0; i < NU; i++) rec[i] = lk[i];
                 failed = true;
                 break;
             }
@@ -746,6 +751,7 @@ __global__ void __launch_bounds__(BP_BLOCK, MINB) k_backpass(Work w, Opts o, Par
             }
         }
         if (failed) {
+            if (o.bp_single) break;   /* back_pass(o) on its own: one attempt, the retry loop belongs to iLQG() */
             raise_lambda(o, lambda, dlambda);
             if (lambda > o.lambdaMax) break;
         } else {
@@ -761,6 +767,7 @@ __global__ void __launch_bounds__(BP_BLOCK, MINB) k_backpass(Work w, Opts o, Par
         g_norm = g_sum / ((double)(T - 1));
         w.g_norm[b] = g_norm;
     }
+    if (o.bp_single) return;
     if (g_norm < o.tolGrad && lambda < 1e-5) { /* iLQG.c:297-303 */
         lower_lambda(o, lambda, dlambda);
         finish(w, b, iter, done ? 1 : 0);
@@ -1064,6 +1071,8 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
                 for (int i = 0; i < NQUU; i++) ws.invH[i] = invH[i];
             }
             if (qp < 1) {
+                double *rec = w.LL[cur] + ((size_t)k * Bp + b) * Rec<P>::RLL;   /* the failed QP's last iterate stays in t->l */
+                for (int e = lane; e < NU; e += 32) rec[e] = lk[e];
                 failed = true;
                 break;
             }
@@ -1176,6 +1185,7 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
         }
         __syncwarp();
         if (failed) {
+            if (o.bp_single) break;
             raise_lambda(o, lambda, dlambda);
             if (lambda > o.lambdaMax) break;
         } else {
@@ -1192,6 +1202,7 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
         g_norm = g_sum / ((double)(T - 1));
         w.g_norm[b] = g_norm;
     }
+    if (o.bp_single) return;
     if (g_norm < o.tolGrad && lambda < 1e-5) {
         lower_lambda(o, lambda, dlambda);
         finish(w, b, iter, done ? 1 : 0);
@@ -1207,9 +1218,13 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
  * first lines of iLQG(), iLQG.c:227-237).  MODE 1 = backtracking line search + accept/reject (line_search.c:33-78,
  * iLQG.c:306-361).
  * ===================================================================================================================== */
-template <class P, bool STORE = true>
+/* number of time segments a recorded rollout can be replayed in (one per lane of a warp) and their length */
+constexpr int LS_SEGS = 32;
+__host__ __device__ inline int ls_seg_len(int T) { return (T + LS_SEGS - 1) / LS_SEGS; }
+
+template <class P, bool STORE = true, bool CKPT = false>
 __device__ __forceinline__ bool rollout(const Work &w, const double *pv, int b, int from, int to, double alpha,
-                                        double w_pen_l, double w_pen_f, double &csum)
+                                        double w_pen_l, double w_pen_f, double &csum, double *ckpt = nullptr)
 {
     constexpr int NX = P::NX, NU = P::NU, RXU = Rec<P>::RXU, RLL = Rec<P>::RLL;
     const size_t Bp = w.Bp;
@@ -1229,7 +1244,15 @@ __device__ __forceinline__ bool rollout(const Work &w, const double *pv, int b, 
         ld_rec<NX + NU>(w.XU[from] + (size_t)b * RXU, nom);
         if (alpha != 0.0) ld_rec<NU + NU * NX>(w.LL[from] + (size_t)b * RLL, ll);
     }
+    const int seg_len = ls_seg_len(T);
+    int next_ck = 0;
     for (int k = 0; k < T; k++) {
+        if (CKPT && k == next_ck) { /* state at the start of every segment: k_ls_commit replays the winner segment-parallel */
+            double *c = ckpt + ((size_t)(k / seg_len) * Bp + b) * NX;
+#pragma unroll
+            for (int i = 0; i < NX; i++) c[i] = x[i];
+            next_ck += seg_len;
+        }
         if (PF) {
             if (k + 1 < T) {
                 ld_rec<PF ? NX + NU : 1>(w.XU[from] + ((size_t)(k + 1) * Bp + b) * RXU, nom_n);
@@ -1306,6 +1329,114 @@ __device__ __forceinline__ bool cost_pass(const Work &w, const double *pv, int b
     return true;
 }
 
+
+/* Steps [k0, k1) of a rollout whose state at step k0 is known (recorded by a checkpointing rollout): the same operations
+ * in the same order as rollout(), hence the same bits, always with stores.  The segment that ends at T also writes the
+ * final record. */
+template <class P>
+__device__ __forceinline__ void rollout_segment(const Work &w, const double *pv, int b, int from, int to, double alpha,
+                                                double w_pen_l, int k0, int k1, const double *xs)
+{
+    constexpr int NX = P::NX, NU = P::NU, RXU = Rec<P>::RXU, RLL = Rec<P>::RLL;
+    const size_t Bp = w.Bp;
+    const int T = w.T;
+    double xu[RXU], xn[NX], mu[P::N_MU_R + P::N_MU_F + 1], nom[RXU], ll[RLL];
+    double *x = xu, *u = xu + NX;
+#pragma unroll
+    for (int i = 0; i < RXU; i++) xu[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NX; i++) x[i] = xs[i];
+    for (int k = k0; k < k1; k++) {
+        ld_rec<NX + NU>(w.XU[from] + ((size_t)k * Bp + b) * RXU, nom);
+        if (alpha != 0.0) {
+            ld_rec<NU + NU * NX>(w.LL[from] + ((size_t)k * Bp + b) * RLL, ll);
+#pragma unroll
+            for (int j = 0; j < NU; j++) u[j] = nom[NX + j] + ll[j] * alpha;
+#pragma unroll
+            for (int i = 0; i < NX; i++) {
+                const double dx = x[i] - nom[i];
+#pragma unroll
+                for (int j = 0; j < NU; j++) u[j] += ll[NU + j + i * NU] * dx;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < NU; j++) u[j] = nom[NX + j];
+        }
+#pragma unroll
+        for (int i = 0; i < P::N_MU_R; i++) mu[i] = w.muR[((size_t)k * P::N_MU_R + i) * Bp + b];
+        double c;
+        P::step(x, u, pv, w.pk, k, T, w_pen_l, mu, xn, c);
+        st_rec<RXU>(w.XU[to] + ((size_t)k * Bp + b) * RXU, xu);
+#pragma unroll
+        for (int i = 0; i < NX; i++) x[i] = xn[i];
+    }
+    if (k1 == T) {
+#pragma unroll
+        for (int j = 0; j < NU; j++) u[j] = 0.0;
+        st_rec<RXU>(w.XU[to] + ((size_t)T * Bp + b) * RXU, xu);
+    }
+}
+
+/* update_multipliers(o, init) of one problem (iLQG_func.tem:417-509) on the trajectory in buffer `buf`.  init = 1 only records
+ * the constraint values: of step 0 for the running constraints -- the reference's early return sits INSIDE the loop over the
+ * steps (iLQG_func.tem:452) -- and of the final ones; it never touches multipliers or penalty weights.  The multiplier
+ * updates use the penalty weights the call started with, like the reference's local copies. */
+template <class P>
+__device__ __forceinline__ void update_mult(const Work &w, const Opts &o, const double *pv, int b, int buf, bool init,
+                                            double &w_pen_l, double &w_pen_f)
+{
+    constexpr int NX = P::NX, NU = P::NU, NR = P::N_MU_R, NF = P::N_MU_F;
+    const size_t Bp = w.Bp;
+    const int T = w.T;
+    double x[NX], u[NU], mu[NR + NF + 1], hval[NR + NF + 1], mun[NR + NF + 1];
+    if (NR > 0) {
+        bool increase = false;
+        const int k_end = init ? (T > 0 ? 1 : 0) : T;
+        for (int k = 0; k < k_end; k++) {
+            double xu[Rec<P>::RXU];
+            ld_rec<NX + NU>(w.XU[buf] + ((size_t)k * Bp + b) * Rec<P>::RXU, xu);
+#pragma unroll
+            for (int i = 0; i < NX; i++) x[i] = xu[i];
+#pragma unroll
+            for (int j = 0; j < NU; j++) u[j] = xu[NX + j];
+#pragma unroll
+            for (int i = 0; i < NR; i++) mu[i] = w.muR[((size_t)k * NR + i) * Bp + b];
+            P::mult_running(x, u, pv, w.pk, k, T, w_pen_l, mu, hval, mun);
+#pragma unroll
+            for (int i = 0; i < NR; i++) {
+                double *last = &w.lastR[((size_t)k * NR + i) * Bp + b];
+                if (i < P::N_MU_LE) {
+                    if (fabs(hval[i]) > o.tolConstraint && o.w_pen_fact1 * fabs(hval[i]) > fabs(*last)) increase = true;
+                } else {
+                    if (hval[i] > o.tolConstraint && o.w_pen_fact1 * hval[i] > *last) increase = true;
+                }
+                *last = hval[i];
+                if (!init) w.muR[((size_t)k * NR + i) * Bp + b] = mun[i];
+            }
+        }
+        if (!init && increase) w_pen_l = dmin(o.w_pen_max_l, w_pen_l * o.w_pen_fact1);
+    }
+    if (NF > 0) {
+        bool increase = false;
+        ld_rec<NX>(w.XU[buf] + ((size_t)T * Bp + b) * Rec<P>::RXU, x);
+#pragma unroll
+        for (int i = 0; i < NF; i++) mu[i] = w.muF[(size_t)i * Bp + b];
+        P::mult_final(x, pv, w.pk, T, T, w_pen_f, mu, hval, mun);
+#pragma unroll
+        for (int i = 0; i < NF; i++) {
+            double *last = &w.lastF[(size_t)i * Bp + b];
+            if (i < P::N_MU_FE) {
+                if (fabs(hval[i]) > o.tolConstraint && o.w_pen_fact1 * fabs(hval[i]) > fabs(*last)) increase = true;
+            } else {
+                if (hval[i] > o.tolConstraint && o.w_pen_fact1 * hval[i] > *last) increase = true;
+            }
+            *last = hval[i];
+            if (!init) w.muF[(size_t)i * Bp + b] = mun[i];
+        }
+        if (!init && increase) w_pen_f = dmin(o.w_pen_max_f, w_pen_f * o.w_pen_fact1);
+    }
+}
+
 enum { INIT_MULT = 1, INIT_ROLLOUT = 2, INIT_BEGIN = 4, INIT_ALL = 7 };
 
 template <class P, bool PP>
@@ -1364,32 +1495,9 @@ __global__ void __launch_bounds__(BP_BLOCK) k_init(Work w, Opts o, ParamBlock<P>
     w.w_pen_l[b] = o.w_pen_init_l;
     w.w_pen_f[b] = o.w_pen_init_f;
     w.new_deriv[b] = 1;
-    if (ok && (P::N_MU_R + P::N_MU_F) > 0) {
-        /* update_multipliers(o, 1): records last_h of step 0 only (running; the early return sits inside the loop,
-           iLQG_func.tem:452) and of the final constraints */
-        double x[P::NX], u[P::NU], mu[P::N_MU_R + P::N_MU_F + 1], hval[P::N_MU_R + P::N_MU_F + 1],
-            mun[P::N_MU_R + P::N_MU_F + 1];
-        if (P::N_MU_R > 0 && T > 0) {
-            double xu[Rec<P>::RXU];
-            ld_rec<P::NX + P::NU>(w.XU[nb] + (size_t)b * Rec<P>::RXU, xu);
-#pragma unroll
-            for (int i = 0; i < P::NX; i++) x[i] = xu[i];
-#pragma unroll
-            for (int i = 0; i < P::NU; i++) u[i] = xu[P::NX + i];
-#pragma unroll
-            for (int i = 0; i < P::N_MU_R; i++) mu[i] = w.muR[(size_t)i * Bp + b];
-            P::mult_running(x, u, pv, w.pk, 0, T, o.w_pen_init_l, mu, hval, mun);
-#pragma unroll
-            for (int i = 0; i < P::N_MU_R; i++) w.lastR[(size_t)i * Bp + b] = hval[i];
-        }
-        if (P::N_MU_F > 0) {
-            ld_rec<P::NX>(w.XU[nb] + ((size_t)T * Bp + b) * Rec<P>::RXU, x);
-#pragma unroll
-            for (int i = 0; i < P::N_MU_F; i++) mu[i] = w.muF[(size_t)i * Bp + b];
-            P::mult_final(x, pv, w.pk, T, T, o.w_pen_init_f, mu, hval, mun);
-#pragma unroll
-            for (int i = 0; i < P::N_MU_F; i++) w.lastF[(size_t)i * Bp + b] = hval[i];
-        }
+    if (ok && (P::N_MU_R + P::N_MU_F) > 0) { /* update_multipliers(o, 1), iLQG.c:236 */
+        double wl = o.w_pen_init_l, wf = o.w_pen_init_f;
+        update_mult<P>(w, o, pv, b, nb, true, wl, wf);
     }
 }
 
@@ -1522,7 +1630,7 @@ k_ls_round(Work w, Opts o, ParamBlock<P> pb, int iter, int round)
  * (problem, alpha), without storing trajectories; k_ls_commit then replays the reference's sequential decision over
  * the recorded costs (first alpha with z > zMin wins, line_search.c:37-60) and re-runs only the winning rollout with
  * stores.  The line search then costs from + 2 rollout latencies instead of n_alpha; results are bit-identical. */
-template <class P, bool PP>
+template <class P, bool PP, bool CKPT>
 __global__ void __launch_bounds__(BP_BLOCK, ILQG_LS_MINBLOCKS) k_ls_tail(Work w, Opts o, ParamBlock<P> pb, int from)
 {
     const int nrem = o.n_alpha - from;
@@ -1540,7 +1648,8 @@ __global__ void __launch_bounds__(BP_BLOCK, ILQG_LS_MINBLOCKS) k_ls_tail(Work w,
     const int cur = w.cur[b];
     const double alpha = o.alpha[a];
     double cnew;
-    const bool ok = rollout<P, false>(w, pv, b, cur, cur ^ 1, alpha, w.w_pen_l[b], w.w_pen_f[b], cnew);
+    const bool ok = rollout<P, false, CKPT>(w, pv, b, cur, cur ^ 1, alpha, w.w_pen_l[b], w.w_pen_f[b], cnew,
+                                            CKPT ? w.ls_ckpt + (size_t)a * LS_SEGS * w.Bp * P::NX : nullptr);
     w.ls_cnew[(size_t)a * w.Bp + b] = cnew;
     if (ok) {
         const double dcost = w.cost[b] - cnew;
@@ -1550,7 +1659,7 @@ __global__ void __launch_bounds__(BP_BLOCK, ILQG_LS_MINBLOCKS) k_ls_tail(Work w,
     }
 }
 
-template <class P, bool PP>
+template <class P, bool PP, bool NOROLL>
 __global__ void __launch_bounds__(BP_BLOCK, ILQG_LS_MINBLOCKS) k_ls_commit(Work w, Opts o, ParamBlock<P> pb, int iter, int from)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1587,7 +1696,7 @@ __global__ void __launch_bounds__(BP_BLOCK, ILQG_LS_MINBLOCKS) k_ls_commit(Work 
     }
     w.n_tail[b] += 1;
     w.n_roll[b] += (win >= 0 ? 1 : 0);
-    if (win >= 0) {
+    if (win >= 0 && !NOROLL) { /* NOROLL: k_ls_commit_seg has stored the winner's trajectory, its cost is the recorded one */
         double c2;
         rollout<P, true>(w, pv, b, cur, cur ^ 1, o.alpha[win], w_pen_l, w_pen_f, c2); /* same arithmetic -> same cost */
         cnew = c2;
@@ -1596,6 +1705,42 @@ __global__ void __launch_bounds__(BP_BLOCK, ILQG_LS_MINBLOCKS) k_ls_commit(Work 
     w.dcost[b] = dcost;
     w.expected[b] = expected;
     ls_decide(w, o, b, iter, cur, win >= 0, win >= 0 ? win + 1 : o.n_alpha + 1, cnew, dcost, w_pen_l, w_pen_f);
+}
+
+
+/* Segment-parallel re-roll of the winners (with k_ls_tail<.., CKPT = true>): thread (problem, segment) -- blockIdx.y is the
+ * segment, lane == position in the problem list exactly as in k_ls_commit, so a warp still reads and writes one contiguous
+ * run of records per step -- re-runs steps [s * seg_len, (s + 1) * seg_len) of the winning rollout from the state the tail
+ * recorded at the start of that segment, with stores.  The re-roll then costs the latency of T / 32 steps instead of T.
+ * Every step repeats the tail's arithmetic on the same inputs, so the stored trajectory is bit-identical to the one the
+ * sequential commit writes; k_ls_commit<.., NOROLL = true> follows with the bookkeeping and takes the cost from the tail's
+ * record.  This kernel only reads solver state. */
+template <class P, bool PP>
+__global__ void __launch_bounds__(BP_BLOCK, ILQG_LS_MINBLOCKS) k_ls_commit_seg(Work w, Opts o, ParamBlock<P> pb, int from)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int seg = blockIdx.y;
+    int b;
+    if (from == 0) {
+        if (tid >= w.B || w.status[tid] != ST_RUNNING) return;
+        b = tid;
+    } else {
+        if (tid >= w.ls_count[from]) return;
+        b = w.ls_list[from & 1][tid];
+    }
+    const int acc = (w.ls_mask[b] >> (16 + from)) & ((1 << (o.n_alpha - from)) - 1);
+    if (!acc) return;
+    const int win = from + (__ffs(acc) - 1);   /* first acceptable alpha (line_search.c:37-60) */
+    const int T = w.T, seg_len = ls_seg_len(T);
+    const int k0 = seg * seg_len, k1 = (k0 + seg_len < T) ? k0 + seg_len : T;
+    if (k0 >= T) return;
+    ILQG_PARAMS(PP, b)
+    const int cur = w.cur[b];
+    double xs[P::NX];
+    const double *c = w.ls_ckpt + (((size_t)win * LS_SEGS + seg) * w.Bp + b) * P::NX;
+#pragma unroll
+    for (int i = 0; i < P::NX; i++) xs[i] = c[i];
+    rollout_segment<P>(w, pv, b, cur, cur ^ 1, o.alpha[win], w.w_pen_l[b], k0, k1, xs);
 }
 
 /* K5: update_multipliers(o, 0) and the cost-only pass that follows an accepted step, or the cost-only pass after a
@@ -1609,64 +1754,82 @@ __global__ void __launch_bounds__(BP_BLOCK) k_post(Work w, Opts o, ParamBlock<P>
     if (mode == POST_NONE) return;
     w.post_mode[b] = POST_NONE;
     ILQG_PARAMS(PP, b)
-    constexpr int NX = P::NX, NU = P::NU, NR = P::N_MU_R, NF = P::N_MU_F;
-    const size_t Bp = w.Bp;
-    const int T = w.T;
     const int cur = w.cur[b];
     double w_pen_l = w.w_pen_l[b], w_pen_f = w.w_pen_f[b];
     if (mode == POST_MULT) {
-        double x[NX], u[NU], mu[NR + NF + 1], hval[NR + NF + 1], mun[NR + NF + 1];
-        if (NR > 0) {
-            bool increase = false;
-            for (int k = 0; k < T; k++) {
-                double xu[Rec<P>::RXU];
-                ld_rec<NX + NU>(w.XU[cur] + ((size_t)k * Bp + b) * Rec<P>::RXU, xu);
-#pragma unroll
-                for (int i = 0; i < NX; i++) x[i] = xu[i];
-#pragma unroll
-                for (int j = 0; j < NU; j++) u[j] = xu[NX + j];
-#pragma unroll
-                for (int i = 0; i < NR; i++) mu[i] = w.muR[((size_t)k * NR + i) * Bp + b];
-                P::mult_running(x, u, pv, w.pk, k, T, w_pen_l, mu, hval, mun);
-#pragma unroll
-                for (int i = 0; i < NR; i++) {
-                    double *last = &w.lastR[((size_t)k * NR + i) * Bp + b];
-                    if (i < P::N_MU_LE) {
-                        if (fabs(hval[i]) > o.tolConstraint && o.w_pen_fact1 * fabs(hval[i]) > fabs(*last)) increase = true;
-                    } else {
-                        if (hval[i] > o.tolConstraint && o.w_pen_fact1 * hval[i] > *last) increase = true;
-                    }
-                    *last = hval[i];
-                    w.muR[((size_t)k * NR + i) * Bp + b] = mun[i];
-                }
-            }
-            if (increase) w_pen_l = dmin(o.w_pen_max_l, w_pen_l * o.w_pen_fact1);
-        }
-        if (NF > 0) {
-            bool increase = false;
-            ld_rec<NX>(w.XU[cur] + ((size_t)T * Bp + b) * Rec<P>::RXU, x);
-#pragma unroll
-            for (int i = 0; i < NF; i++) mu[i] = w.muF[(size_t)i * Bp + b];
-            P::mult_final(x, pv, w.pk, T, T, w_pen_f, mu, hval, mun);
-#pragma unroll
-            for (int i = 0; i < NF; i++) {
-                double *last = &w.lastF[(size_t)i * Bp + b];
-                if (i < P::N_MU_FE) {
-                    if (fabs(hval[i]) > o.tolConstraint && o.w_pen_fact1 * fabs(hval[i]) > fabs(*last)) increase = true;
-                } else {
-                    if (hval[i] > o.tolConstraint && o.w_pen_fact1 * hval[i] > *last) increase = true;
-                }
-                *last = hval[i];
-                w.muF[(size_t)i * Bp + b] = mun[i];
-            }
-            if (increase) w_pen_f = dmin(o.w_pen_max_f, w_pen_f * o.w_pen_fact1);
-        }
+        update_mult<P>(w, o, pv, b, cur, false, w_pen_l, w_pen_f);
         w.w_pen_l[b] = w_pen_l;
         w.w_pen_f[b] = w_pen_f;
     }
     double csum;
     cost_pass<P>(w, pv, b, cur, w_pen_l, w_pen_f, csum);
     w.cost[b] = csum;
+}
+
+
+/* update_multipliers(o, init) on its own (iLQG.h:86), for every running problem: the single-problem drop-in's entry point */
+template <class P, bool PP>
+__global__ void __launch_bounds__(BP_BLOCK) k_mult(Work w, Opts o, ParamBlock<P> pb, int init)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= w.B || w.status[b] != ST_RUNNING) return;
+    ILQG_PARAMS(PP, b)
+    double w_pen_l = w.w_pen_l[b], w_pen_f = w.w_pen_f[b];
+    update_mult<P>(w, o, pv, b, w.cur[b], init != 0, w_pen_l, w_pen_f);
+    w.w_pen_l[b] = w_pen_l;
+    w.w_pen_f[b] = w_pen_f;
+}
+
+/* The dense per-step record the backward pass works on (fx fu cx cxx cu cuu cxu lower upper lower_sign upper_sign lower_hx
+ * upper_hx: the derivative members of trajEl_t, iLQG_problem.tem:23-51), rebuilt from the time-varying entries of the last
+ * derivative sweep and the parameters: out[b][k][DENSE_SIZE].  Read-back path of calc_derivs for the drop-in and for tests. */
+template <class P, bool PP>
+__global__ void __launch_bounds__(DV_BLOCK) k_dense(Work w, ParamBlock<P> pb, double *out)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (b >= w.B) return;
+    ILQG_PARAMS(PP, b)
+    const size_t Bp = w.Bp;
+    Dense<P> D;
+    double *Dd = reinterpret_cast<double *>(&D);
+#pragma unroll
+    for (int i = 0; i < P::DENSE_SIZE; i++) Dd[i] = 0.0;
+    P::consts(pv, D);
+    double v1[P::NV1];
+    if (use_coop<P>()) {
+        const double *r = w.V1 + ((size_t)k * Bp + b) * P::NV1;
+#pragma unroll
+        for (int i = 0; i < P::NV1; i++) v1[i] = r[i];
+    } else {
+        const double *r = w.V1 + (size_t)k * P::NV1 * Bp + b;
+#pragma unroll
+        for (int i = 0; i < P::NV1; i++) v1[i] = r[i * Bp];
+    }
+    P::unpack(v1, D);
+    double *o_ = out + ((size_t)b * w.T + k) * P::DENSE_SIZE;
+#pragma unroll
+    for (int i = 0; i < P::DENSE_SIZE; i++) o_[i] = Dd[i];
+}
+
+/* clampU(u, t, k, p, N) (iLQG_func.tem:68-73) for a batch: xu[b] = x | u, the clamped u is written back in place */
+template <class P, bool PP>
+__global__ void __launch_bounds__(BP_BLOCK) k_clamp(Work w, ParamBlock<P> pb, double *xu_io, int k)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= w.B) return;
+    ILQG_PARAMS(PP, b)
+    double x[P::NX], u[P::NU], xn[P::NX], mu[P::N_MU_R + P::N_MU_F + 1], c;
+    double *io = xu_io + (size_t)b * (P::NX + P::NU);
+#pragma unroll
+    for (int i = 0; i < P::NX; i++) x[i] = io[i];
+#pragma unroll
+    for (int i = 0; i < P::NU; i++) u[i] = io[P::NX + i];
+#pragma unroll
+    for (int i = 0; i < P::N_MU_R; i++) mu[i] = 0.0;
+    P::step(x, u, pv, w.pk, k, w.T, 0.0, mu, xn, c);   /* the clamp is the first thing a step does to u */
+#pragma unroll
+    for (int i = 0; i < P::NU; i++) io[P::NX + i] = u[i];
 }
 
 /* after the last pass: problems still running hit the iteration limit (iLQG.c:365-377) */

@@ -16,6 +16,9 @@ typedef struct ilqg_opts {
     int bp_latency_build; /* backward pass: 1 = register-unconstrained build (small batches), 0 = 128-register build */
     int ls_tail_from;   /* line search: rounds [0, ls_tail_from) run one alpha per launch, the remaining alphas all at once;
                            >= n_alpha: purely sequential rounds (large batches) */
+    int bp_single;      /* backward pass: 1 = one attempt at the current lambda, no retry, no exit test (back_pass(o) on its own) */
+    int ls_commit_par;  /* 1: the tail records the state at the start of 32 time segments and the commit replays the
+                           winner segment-parallel (one warp per problem); 0: the commit re-rolls the winner sequentially */
 } ilqg_opts;
 
 /* device workspace of one batch; all arrays are [..][Bp] with the problem index fastest */
@@ -34,6 +37,8 @@ typedef struct ilqg_work {
     int *ls_list[2], *ls_count; /* line search: compacted lists of undecided problems (ping-pong), per-round counts */
     double *ls_cnew;            /* [MAX_ALPHA][Bp] rollout cost per alpha (parallel tail of the line search) */
     int *ls_mask;               /* [Bp] bit a: rollout of alpha a finite; bit 16+a: alpha a acceptable */
+    double *ls_ckpt;            /* [MAX_ALPHA][32][Bp][NX] state at the start of each time segment of the tail's rollouts
+                                   (null: the commit re-rolls the winner sequentially) */
     int *n_dv, *n_roll, *n_tail; /* work counters (bench roofline accounting): derivative sweeps consumed, rollouts that
                                   stored a trajectory, parallel-alpha tails (one shared read of the nominal, no stores) */
     /* optional traces for parity tests (null when disabled) */

@@ -97,6 +97,19 @@ int ilqgb_download(ilqgb_handle *h, double *x, double *u, double *cost, int *ite
 int ilqgb_phase_derivs(ilqgb_handle *h);
 int ilqgb_phase_backpass(ilqgb_handle *h);
 int ilqgb_phase_linesearch(ilqgb_handle *h);
+/* back_pass(o) exactly (back_pass.h:7): ONE attempt at the current lambda -- no regularisation retry (iLQG.c:261-284), no
+ * gradient exit (iLQG.c:297-303); success = ilqgb_get_int "bp_done".  update_multipliers(o, init) (iLQG.h:86) and
+ * clampU(u, t, k, p, N) (iLQG_func.tem:68) for every problem of the batch: x [batch][nx], u [batch][nu] clamped in place. */
+int ilqgb_phase_backpass_once(ilqgb_handle *h);
+int ilqgb_phase_multipliers(ilqgb_handle *h, int init);
+int ilqgb_clamp_u(ilqgb_handle *h, int k, const double *x, double *u);
+/* "dense" field of ilqgb_get: [batch][n_hor][ilqgb_dense_size()] = fx fu cx cxx cu cuu cxu lower upper lower_sign upper_sign
+ * lower_hx upper_hx of every step (the derivative members of trajEl_t) as the backward pass sees them */
+int ilqgb_dense_size(void);
+/* run-time tuning knobs, otherwise chosen from the batch size: "ls_tail_from" (sequential line-search rounds before the
+ * parallel-alpha tail; >= n_alpha: all rounds sequential, every tried rollout is stored as in the reference), "bp_latency";
+ * "pass_index": the loop index the next ilqgb_phase_* call runs as (row of the traces) */
+int ilqgb_set_tuning(ilqgb_handle *h, const char *name, int value);
 
 /* field read-back (synchronises). Per-problem scalars: "cost" "new_cost" "dcost" "expected" "lambda" "dlambda"
  * "g_norm" "dV0" "dV1" "w_pen_l" "w_pen_f" -> [batch].  Trajectory fields, problem-major [batch][k][i]:
@@ -105,12 +118,12 @@ int ilqgb_phase_linesearch(ilqgb_handle *h);
  * "v1" "v2" "fd" hold the derivatives of the last sweep that covered the problem; for a problem that has finished they may
  * have been re-evaluated at its final trajectory by a later sweep (they are never read again by the solver). */
 long ilqgb_get(ilqgb_handle *h, const char *field, double *out);
-/* "iterations" "result" "status" "n_linesearch" "n_backpass" "n_derivs" "n_rollouts" "n_tails" "cur" -> [batch]; "tr_alpha" -> [batch][max_iter];
+/* "iterations" "result" "status" "n_linesearch" "n_backpass" "n_derivs" "n_rollouts" "n_tails" "cur" "bp_done" "deriv_fail" -> [batch]; "tr_alpha" -> [batch][max_iter];
  * "tr_clamp" -> [batch][n_hor] (2 bits per input: 0 free, 1 lower, 2 upper; QP return code in bits 16..23) */
 long ilqgb_get_int(ilqgb_handle *h, const char *field, int *out);
 
 /* host -> device write of a field (names and shapes of ilqgb_get, plus "x0" "x_cand" "u_cand" "last_r" "last_f";
- * ints: "cur" "status"), a solve start on imported state (only the first lines of iLQG(), iLQG.c:226-237, run), and a
+ * ints: "cur" "status" "new_deriv" "deriv_fail" "bp_done"), a solve start on imported state (only the first lines of iLQG(), iLQG.c:226-237, run), and a
  * bare rollout = forward_pass(candidates[0] or nominal, o, alpha, &csum, cost_only) of iLQG.h:82: csum -> "new_cost",
  * its return value -> "result".  These carry the single-problem drop-in (csrc/ilqg_dropin.c). */
 long ilqgb_put(ilqgb_handle *h, const char *field, const double *in);

@@ -11,7 +11,7 @@
 #include <pthread.h>
 
 #include "iLQG.h"
-#ifndef H_NO_PHASES
+#ifndef H_NO_PHASES /* the solver's phases are public functions of the reference (back_pass.h:7, line_search.h:6) */
 #include "line_search.h"
 #include "back_pass.h"
 #include "boxQP.h"
@@ -165,6 +165,10 @@ int h_back_pass(HSolver *s) { (void)s; return -1; }
 int h_line_search(HSolver *s, int iter) { (void)s; (void)iter; return -1; }
 int h_update_multipliers(HSolver *s, int init) { (void)s; (void)init; return -1; }
 #endif
+#ifndef H_NO_PHASES
+/* clampU on step k of the nominal trajectory (its state-dependent auxiliaries are those of the last forward pass) */
+void h_clamp_u(HSolver *s, int k, double *u) { clampU(u, &s->o.nominal->t[k], k, s->o.p, s->o.n_hor); }
+#endif
 int h_forward_pass(HSolver *s, double alpha, double *csum, int cost_only)
 {
     g_cur = s;
@@ -265,7 +269,7 @@ int h_get(HSolver *s, const char *field, double *out)
     return -1;
 }
 
-#ifndef H_NO_PHASES
+#if !defined(H_NO_PHASES) && !defined(H_NO_SPY_FUNCS)
 /* ---- spies ------------------------------------------------------------------------------------------------ */
 int h_spy_line_search(tOptSet *o, int iter)
 {
