@@ -1807,6 +1807,15 @@ __global__ void __launch_bounds__(DV_BLOCK) k_dense(Work w, ParamBlock<P> pb, do
         for (int i = 0; i < P::NV1; i++) v1[i] = r[i * Bp];
     }
     P::unpack(v1, D);
+    if (!P::HAS_HX) { /* limitsU also records which side is bounded (iLQG_func.tem:101-118); the solver itself needs the signs only
+                         together with state-dependent limits, so they are not part of the stored entries otherwise */
+        const double inf = dm_from_bits(0x7ff0000000000000ull);
+#pragma unroll
+        for (int i = 0; i < P::NU; i++) {
+            D.lower_sign[i] = (D.lower[i] == -inf) ? 0.0 : -1.0;
+            D.upper_sign[i] = (D.upper[i] == inf) ? 0.0 : 1.0;
+        }
+    }
     double *o_ = out + ((size_t)b * w.T + k) * P::DENSE_SIZE;
 #pragma unroll
     for (int i = 0; i < P::DENSE_SIZE; i++) o_[i] = Dd[i];

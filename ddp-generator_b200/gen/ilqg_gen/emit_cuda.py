@@ -194,7 +194,10 @@ def emit_device(m, struct_name) -> str:
     def derivs_body(full):
         sc = Scope("d")
         aux_outs(sc, m.aux, lambda a: a.used_running)
-        aux_outs(sc, m.daux, lambda a: a.used_running and (full or _needed_first(a)))
+        # calcLAuxDeriv evaluates -- and guards -- EVERY auxiliary derivative whatever FULL_DDP is (iLQG_func.tem:252-260: only
+        # the fxx/fuu/fxu blocks sit under #if FULL_DDP), so a non-finite second-order auxiliary derivative fails calc_derivs
+        # of a FULL_DDP=0 build too.  The first-order-only variant therefore still evaluates them, for their guards alone.
+        aux_outs(sc, m.daux, lambda a: a.used_running and (full or _needed_first(a) or not a.atomic))
         for key, e in v1:
             sc.out(("v1", v1_pos[(key, e.idx)]), e.expr, not e.atomic)
         if full:
