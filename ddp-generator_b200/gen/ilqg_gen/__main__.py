@@ -29,13 +29,28 @@ def generate(name, outdir, mac=None):
     return m
 
 
-if __name__ == "__main__":
-    if len(sys.argv) == 5 and sys.argv[1] == "--mac":      # python -m ilqg_gen --mac file.mac <name> <outroot>
-        generate(sys.argv[3], os.path.join(sys.argv[4], sys.argv[3]), mac=sys.argv[2])
-        print("generated", sys.argv[3], "from", sys.argv[2])
-        sys.exit(0)
-    names = sys.argv[1:-1] if len(sys.argv) > 2 else list(REGISTRY)
-    root = sys.argv[-1] if len(sys.argv) > 1 else "."
-    for n in names:
-        generate(n, os.path.join(root, n))
+def main(argv=None):
+    import argparse
+
+    ap = argparse.ArgumentParser(prog="python -m ilqg_gen", description="Generate iLQG_problem.h, iLQG_func.c and <name>_device.cuh "
+                                 "for built-in problem modules or for a reference-style Maxima problem file.")
+    ap.add_argument("--mac", metavar="FILE.mac", help="read the problem from a .mac file; exactly one NAME must follow")
+    ap.add_argument("names", nargs="*", metavar="NAME", help=f"problems to generate (default: all of {', '.join(REGISTRY)})")
+    ap.add_argument("outroot", help="output root; files go to <outroot>/<name>/")
+    a = ap.parse_args(argv)
+    if a.mac:
+        if len(a.names) != 1:
+            ap.error("--mac needs exactly one NAME")
+        generate(a.names[0], os.path.join(a.outroot, a.names[0]), mac=a.mac)
+        print("generated", a.names[0], "from", a.mac)
+        return
+    unknown = [n for n in a.names if n not in REGISTRY]
+    if unknown:
+        ap.error(f"unknown problem(s) {unknown}; built-in: {sorted(REGISTRY)}")
+    for n in a.names or list(REGISTRY):
+        generate(n, os.path.join(a.outroot, n))
         print("generated", n)
+
+
+if __name__ == "__main__":
+    main()

@@ -14,6 +14,7 @@ Every other undefined identifier is a parameter: `p` a scalar, `p[3]` an array e
 """
 from __future__ import annotations
 
+import ast
 import re
 
 import sympy as sp
@@ -50,6 +51,40 @@ class _ParamArray:
 def _statements(text):
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return [s.strip() for s in re.split(r"[;$]", text) if s.strip()]
+
+
+_AST_OK = (ast.Expression, ast.BinOp, ast.UnaryOp, ast.Call, ast.Name, ast.Constant, ast.Subscript, ast.Load, ast.Add, ast.Sub,
+           ast.Mult, ast.Div, ast.Pow, ast.USub, ast.UAdd)
+
+
+class _ExactInts(ast.NodeTransformer):
+    """Integer literals become exact sympy Integers, as in Maxima: 2/3 is a rational and p^(1/2) a square root, not Python's
+    float division.  Subscripts (cf[2], ymin[k]) keep plain ints."""
+
+    def visit_Subscript(self, node):
+        node.value = self.visit(node.value)
+        return node
+
+    def visit_Constant(self, node):
+        if isinstance(node.value, int) and not isinstance(node.value, bool):
+            return ast.copy_location(ast.Call(func=ast.Name(id="_I", ctx=ast.Load()), args=[node], keywords=[]), node)
+        return node
+
+
+def _safe_tree(text):
+    """Expression text -> code tree restricted to arithmetic, names, calls of plain names and subscripts.  Attribute access,
+    comprehensions, lambdas, strings ... are rejected, so a problem file cannot reach anything but the maths namespace."""
+    tree = ast.parse(text.strip(), mode="eval")
+    for node in ast.walk(tree):
+        if not isinstance(node, _AST_OK):
+            raise ValueError(f"unsupported syntax in problem file expression: {type(node).__name__} in {text.strip()[:60]!r}")
+        if isinstance(node, ast.Call) and (not isinstance(node.func, ast.Name) or node.keywords):
+            raise ValueError(f"only plain function calls are allowed in problem file expressions: {text.strip()[:60]!r}")
+        if isinstance(node, ast.Constant) and not isinstance(node.value, (int, float)):
+            raise ValueError(f"unsupported literal in problem file expression: {node.value!r}")
+        if isinstance(node, ast.Name) and node.id.startswith("__") and not node.id.startswith("__aux_"):
+            raise ValueError(f"unsupported name {node.id!r} in problem file expression")
+    return ast.fix_missing_locations(_ExactInts().visit(tree))
 
 
 def load_mac(path, name=None):
@@ -99,7 +134,8 @@ def load_mac(path, name=None):
                 raise ValueError(f"'{nm} used before it is defined")
             env["__aux_" + nm] = values[nm][1]
         env["integrate"] = lambda ex, var, a, b: sp.integrate(ex, (var, a, b))
-        return sp.sympify(eval(compile(e, "<mac>", "eval"), {"__builtins__": {}}, env))  # noqa: S307 (trusted problem file)
+        env["_I"] = sp.Integer
+        return sp.sympify(eval(compile(_safe_tree(e), "<mac>", "eval"), {"__builtins__": {}}, env))  # noqa: S307 (whitelisted AST)
 
     lists = {}
     for s in stmts:

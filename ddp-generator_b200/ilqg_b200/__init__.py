@@ -24,8 +24,8 @@ _SCALAR_FIELDS = {"cost", "new_cost", "dcost", "expected", "lambda", "dlambda", 
                   "iterations", "result", "status", "n_linesearch", "n_backpass", "n_derivs", "n_rollouts", "n_tails", "cur"}
 
 
-def lib_path(problem, full_ddp):
-    return os.path.join(LIB_DIR, f"libilqg_b200_{problem}_ddp{int(full_ddp)}.so")
+def lib_path(problem, full_ddp, lib_dir=None):
+    return os.path.join(lib_dir or LIB_DIR, f"libilqg_b200_{problem}_ddp{int(full_ddp)}.so")
 
 
 def _ptr(a):
@@ -37,16 +37,16 @@ class Library:
 
     _cache = {}
 
-    def __new__(cls, problem, full_ddp):
-        key = (problem, int(full_ddp))
+    def __new__(cls, problem, full_ddp, lib_dir=None):
+        key = (problem, int(full_ddp), lib_dir)
         if key not in cls._cache:
             self = super().__new__(cls)
-            self._load(problem, full_ddp)
+            self._load(problem, full_ddp, lib_dir)
             cls._cache[key] = self
         return cls._cache[key]
 
-    def _load(self, problem, full_ddp):
-        path = lib_path(problem, full_ddp)
+    def _load(self, problem, full_ddp, lib_dir=None):
+        path = lib_path(problem, full_ddp, lib_dir)
         if not os.path.exists(path):
             raise RuntimeError(f"{path} not found: build it with `make -C ddp-generator_b200` (no CPU fallback exists)")
         L = self.lib = C.CDLL(path)
@@ -104,10 +104,11 @@ class Library:
 
 
 class BatchSolver:
-    def __init__(self, problem, full_ddp=0, batch=1, n_hor=1, device=0, flags=0, stream=None, chunks=0, devices=None):
+    def __init__(self, problem, full_ddp=0, batch=1, n_hor=1, device=0, flags=0, stream=None, chunks=0, devices=None, lib_dir=None):
         """`devices`: list of GPU indices (or a count) to shard the batch over in this one process (ilqgb_create_multi);
-        `chunks` then counts chunks per device.  Default: the single GPU `device`."""
-        self.L = Library(problem, full_ddp)
+        `chunks` then counts chunks per device.  Default: the single GPU `device`.  `lib_dir`: where the problem's library was
+        built (python -m ilqg_gen.make --out DIR puts it in DIR/lib); default: the package's lib/."""
+        self.L = Library(problem, full_ddp, lib_dir)
         self.lib = self.L.lib
         self.B, self.T = int(batch), int(n_hor)
         self.nx, self.nu = self.L.nx, self.L.nu

@@ -65,6 +65,6 @@ def test_no_cpu_fallback():
 
 def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(ilqg_b200, "LIB_DIR", "/nonexistent")
-    ilqg_b200.Library._cache.pop(("quadx", 0), None)
+    ilqg_b200.Library._cache.pop(("quadx", 0, None), None)
     with pytest.raises(RuntimeError, match="not found"):
         ilqg_b200.Library("quadx", 0)

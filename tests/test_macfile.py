@@ -115,3 +115,24 @@ def test_f_must_be_indexed_by_states_and_k_index_cannot_be_mixed():
         open(path, "w").write(_BAD.replace("L: a^2 + w^2;", "L: r[k]*a^2 + r[1]*w^2;") % "")
         with pytest.raises(ValueError, match="index k and other integer index mixed"):      # genenerator_main.mac:146-152
             load_mac(path)
+
+
+def test_mac_expressions_are_exact_and_sandboxed(tmp_path):
+    """Integer arithmetic follows Maxima (2/3 is a rational, p^(1/2) a square root -> sqrt in the generated code), and an
+    expression can only use arithmetic, plain calls and subscripts: no attribute access, comprehensions, lambdas, strings."""
+    base = "x: [y];\nu: [dy];\nf[y]: y + dy*dx;\nL: %s;\nF: 0;\n"
+    f = tmp_path / "t.mac"
+    f.write_text(base % "(2/3)*dy^2 + p^(1/2)*y^2")
+    P = load_mac(str(f), "T")
+    assert sp.simplify(P.L - (sp.Rational(2, 3) * P.u[0] ** 2 + sp.sqrt(sp.Symbol("p", real=True)) * P.x[0] ** 2)) == 0
+    assert "dm_sqrt(p[1][0])" in emit_func_c(lower(P))
+    for bad in ("y.__class__", "[c for c in y]", "(lambda: 1)()", "__import__(1)", "'a'"):
+        f.write_text(base % bad)
+        with pytest.raises(ValueError):
+            load_mac(str(f), "T")
+
+
+def test_generator_cli_has_help(tmp_path):
+    r = subprocess.run(["python", "-m", "ilqg_gen", "--help"], capture_output=True, text=True, cwd=str(tmp_path),
+                       env=dict(os.environ, PYTHONPATH=os.path.join(ROOT, "ddp-generator_b200", "gen")))
+    assert r.returncode == 0 and "outroot" in r.stdout and not os.listdir(str(tmp_path))
