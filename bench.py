@@ -330,11 +330,14 @@ def short_config(tag, problem, ddp, B, T, params, inputs, max_iter, sample_n, de
     torch.cuda.synchronize()
     time.sleep(IDLE_S)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall = time.perf_counter()
     e0.record()
     S.run()
     e1.record()
     torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall
     ms = e0.elapsed_time(e1)
+    assert stream != 0 and 0.8 * t_wall * 1e3 <= ms <= 1.02 * t_wall * 1e3, (ms, t_wall)
     launches = S.launch_count() - l0
     S.download_ptr(None, None, co.data_ptr(), io.data_ptr(), ro.data_ptr(), no.data_ptr())
     n_ls = int(no.numpy().sum())
@@ -441,7 +444,12 @@ def main():
 
     from ilqg_b200 import workloads as W
 
+    # The library's streams are non-blocking: they do NOT order with the legacy default stream, so events recorded there would
+    # not bracket the solve (round 1 did that and under-measured the timed region: its event fired when the last passes were
+    # ISSUED).  Everything here runs on one explicit stream that the handle adopts as its main stream (fork / join point).
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
     stream = torch.cuda.current_stream().cuda_stream
+    assert stream != 0
     S = ilqg_b200.BatchSolver(PROBLEM, FULL_DDP, count, T_HOR, device=local_rank, flags=0, stream=stream, chunks=args.chunks,
                               devices=multi or None)
     S.set_params(W.CAR_PARAMS)
@@ -463,12 +471,16 @@ def main():
     sampler.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall = time.perf_counter()
     e0.record()
     S.run()
     e1.record()
     barrier()
+    t_wall = time.perf_counter() - t_wall
     clocks = sampler.stop()
     ms_dev = e0.elapsed_time(e1)
+    if not (0.8 * t_wall * 1e3 <= ms_dev <= 1.02 * t_wall * 1e3):   # the events must bracket the work the host waited for
+        raise SystemExit(f"bench.py: device time {ms_dev:.1f} ms does not match the wall clock {t_wall * 1e3:.1f} ms around the same region")
     launches = S.launch_count() - launches0
     S.download_ptr(None, None, cost_out.data_ptr(), it_out.data_ptr(), res_out.data_ptr(), nls_out.data_ptr())
     n_ls = int(nls_out.numpy().sum())
@@ -556,7 +568,7 @@ def main():
                     "d2h_bytes_per_step": d2h_tot / max(args.steps, 1), "h2d_bytes": h2d_tot, "d2h_bytes": d2h_tot,
                     "seconds": ms_e2e_max * 1e-3, "clocks": eclocks},
             "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
-            "iterations_total": its_total, "seconds": ms_max * 1e-3, "deterministic_rerun": deterministic,
+            "iterations_total": its_total, "seconds": ms_max * 1e-3, "seconds_wall_rank0": t_wall, "deterministic_rerun": deterministic,
             "streams_per_gpu": chunks_per_gpu, "process_model": "one process, ilqgb_create_multi" if multi else "one process per GPU",
             "extra": extra,
         }

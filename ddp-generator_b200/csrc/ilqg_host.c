@@ -1011,13 +1011,14 @@ struct ilqgb_handle {
 
 static int auto_chunks(int batch)
 {
-    /* measured on B200 (scripts/gpu_probe_e2e.py, car, 20 passes): chunks of about 32 768 problems, at most eight, and two
-       from 16 384 problems on.  Resident solves are insensitive to the count (262 144 problems: 4 chunks 8.24 M it/s, 6: 8.11 M,
-       8: 8.12 M; 32 768: 1 chunk 5.39 M, 2: 5.47-5.56 M, 4: 5.43-5.53 M, 8: 5.02 M); end to end more, smaller chunks
-       shorten the exposed first upload and last download (262 144: 4 chunks 7.33 M, 8: 7.50 M; 32 768: 1 chunk 4.62 M, 2: 4.93 M). */
-    int n = batch / 32768;
+    /* measured on B200 (scripts/gpu_probe_e2e.py, car, 20 passes, 262 144 problems; resident s / end-to-end s): 2 chunks 0.656 / 0.763,
+       4 chunks 0.645 / 0.711, 8 chunks 0.673 / 0.718, 16 chunks 0.679 / 0.720 (end to end on prioritised streams; with equal
+       priorities 4 chunks 0.729, 8 chunks 0.734).  32 768 problems: 1 chunk 0.121 / 0.142, 2 chunks 0.118-0.120 / 0.133, 4 chunks
+       0.119-0.121 / 0.132-0.134, 8 chunks 0.131 / 0.138.  So: chunks of about 65 536 problems, at most four, and two from 16 384
+       problems on, so that an end-to-end solve has something to overlap its copies with. */
+    int n = batch / 65536;
     if (n < 2) n = batch >= 16384 ? 2 : 1;
-    if (n > 8) n = 8;
+    if (n > 4) n = 4;
     return n;
 }
 

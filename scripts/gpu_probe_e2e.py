@@ -16,6 +16,7 @@ from ilqg_b200 import workloads as W
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 262144
 STEPS = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 T = 500
+IDLE = float(os.environ.get("IDLE", "1.5"))   # seconds of idle before every timed call (bench.py's regime); 0 = back to back
 res = {"B": B, "steps": STEPS, "runs": []}
 
 # PCIe copy rates with pinned memory (what the DMA path can do at best)
@@ -78,12 +79,15 @@ for chunks, prio, stagger in sweep:
     S.set_options({"max_iter": STEPS})
     S.upload_ptr(x0.data_ptr(), u0.data_ptr()); S.sync()
     torch.cuda.synchronize()
+    time.sleep(IDLE)
     t0 = time.perf_counter(); S.run(); S.sync(); t_res = time.perf_counter() - t0
     S.download_ptr(None, None, co.data_ptr(), io.data_ptr(), ro.data_ptr(), no.data_ptr())
     nls = int(no.numpy().sum())
     cost_res = co.numpy().copy()
     te = []
+    S.solve_host_ptr(x0.data_ptr(), u0.data_ptr(), xo.data_ptr(), uo.data_ptr(), co.data_ptr(), io.data_ptr(), ro.data_ptr(), no.data_ptr())   # warm-up (staging buffers)
     for _ in range(2):
+        time.sleep(IDLE)
         t0 = time.perf_counter()
         S.solve_host_ptr(x0.data_ptr(), u0.data_ptr(), xo.data_ptr(), uo.data_ptr(), co.data_ptr(), io.data_ptr(), ro.data_ptr(), no.data_ptr())
         te.append(time.perf_counter() - t0)

@@ -229,7 +229,7 @@ def test_non_finite_rollouts_inside_the_line_search(tail_from, monkeypatch):
 
 
 def test_config4_full_size_sample_parity():
-    """BASELINE config 4 at full size (262 144 car problems, T = 500; 8 concurrent chunks): problems next to every chunk
+    """BASELINE config 4 at full size (262 144 car problems, T = 500; 4 concurrent chunks): problems next to every chunk
     boundary and at both ends match the oracle bit for bit; a rerun is bit-identical."""
     B, T, iters = 262144, 500, 4
     x0 = np.empty((B, 4)); u0 = np.empty((B, T, 2))
@@ -237,12 +237,12 @@ def test_config4_full_size_sample_parity():
         a, b = W.car_batch(32768, T=T, first=s0)
         x0[s0:s0 + 32768] = a; u0[s0:s0 + 32768] = b
     s = ilqg_b200.BatchSolver("car", 0, B, T)
-    assert s.chunks() == 8
+    assert s.chunks() == 4
     s.set_options({"max_iter": iters}); s.set_params(W.CAR_PARAMS)
     out = s.solve(x0, u0, want_traj=False)
     cost_again = s.solve(x0, u0, want_traj=False)["cost"]
     assert np.array_equal(out["cost"], cost_again)
-    idx = np.concatenate([np.arange(0, 8)] + [np.arange(c * 32768 - 3, c * 32768 + 3) for c in range(1, 8)] + [np.arange(B - 8, B)])
+    idx = np.concatenate([np.arange(0, 8)] + [np.arange(c * 65536 - 3, c * 65536 + 3) for c in range(1, 4)] + [np.arange(B - 8, B)])
     xs = s.get("x")[idx]
     s.close()
     ora = _oracle("car", 0).solve_batch(x0[idx], u0[idx], W.CAR_PARAMS, {"max_iter": float(iters)}, 4, want_traj=True)
