@@ -122,8 +122,23 @@ int ilqgk_launch_derivs(const ilqg_work *w, const double *params, void *stream)
 
 int ilqgk_launch_backpass(const ilqg_work *w, const ilqg_opts *o, const double *params, int iter, void *stream)
 {
-    if constexpr (use_coop<P>())
-        PP_DISPATCH(w, (k_backpass_warp<P, FULL_DDP != 0, PP><<<nblk(w->B, CW_WARPS), CW_WARPS * 32, 0, (cudaStream_t)stream>>>(*w, *o, make_pb(params), iter)));
+    if constexpr (use_coop<P>()) {
+        /* lanes per problem: 32, 16 or 8 (o->cw_lpp); the workspace of all problems of a block sits in dynamic shared memory */
+        static unsigned char cw_configured[ILQGK_MAX_DEVICES];
+        int dev = 0;
+        if (check(cudaGetDevice(&dev), "cudaGetDevice")) return -1;
+#define CW_ATTR(LPP_, PP_) check(cudaFuncSetAttribute(k_backpass_warp<P, FULL_DDP != 0, PP_, LPP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem_bytes<P, LPP_>()), "cudaFuncSetAttribute")
+        if (dev < 0 || dev >= ILQGK_MAX_DEVICES || !cw_configured[dev]) {
+            if (CW_ATTR(32, false) || CW_ATTR(32, true) || CW_ATTR(16, false) || CW_ATTR(16, true) || CW_ATTR(8, false) || CW_ATTR(8, true)) return -1;
+            if (dev >= 0 && dev < ILQGK_MAX_DEVICES) cw_configured[dev] = 1;
+        }
+#undef CW_ATTR
+#define CW_LAUNCH(LPP_) PP_DISPATCH(w, (k_backpass_warp<P, FULL_DDP != 0, PP, LPP_><<<nblk(w->B, CW_WARPS * (32 / LPP_)), CW_WARPS * 32, coop_smem_bytes<P, LPP_>(), (cudaStream_t)stream>>>(*w, *o, make_pb(params), iter)))
+        if (o->cw_lpp == 8) CW_LAUNCH(8);
+        else if (o->cw_lpp == 16) CW_LAUNCH(16);
+        else CW_LAUNCH(32);
+#undef CW_LAUNCH
+    }
     else {
         constexpr size_t smem = sizeof(double) * 2 * bp_fields<P, FULL_DDP != 0>() * BP_BLOCK;
         /* the opt-in to > 48 KB dynamic shared memory is a per-device function attribute: applied once on every device

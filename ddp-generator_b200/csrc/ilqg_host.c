@@ -50,6 +50,7 @@ struct chunk {
     int gate_recorded;
     int ls_tail_from;      /* -1 = choose by batch size */
     int bp_latency;        /* -1 = choose by batch size */
+    int cw_lpp;            /* warp-cooperative backward pass: lanes per problem */
     int total_B;           /* problems of the whole handle (all chunks run concurrently on one GPU) */
     int started;
     int trace_cap;         /* max_iter the trace arrays were sized for */
@@ -358,6 +359,7 @@ static chunk *ck_create(int device, int batch, int n_hor, int flags, void *strea
     h->flags = flags;
     h->ls_tail_from = getenv("ILQG_LS_TAIL_FROM") ? atoi(getenv("ILQG_LS_TAIL_FROM")) : -1;
     h->bp_latency = getenv("ILQG_BP_LATENCY") ? atoi(getenv("ILQG_BP_LATENCY")) : -1;
+    h->cw_lpp = env_int("ILQG_CW_LPP", 32);
     ilqgk_dims(&h->d);
     if (h->d.nkp > 16) {
         fail(NULL, "too many [k]-indexed parameters");
@@ -701,6 +703,7 @@ static int launch_pass(chunk *h, int do_derivs, int do_back, int do_ls)
     if (do_back) {
         p = timing_begin(h, TC_BACKPASS);
         h->o.bp_latency_build = h->bp_latency >= 0 ? h->bp_latency : (h->total_B <= 40000);
+        h->o.cw_lpp = h->cw_lpp;
         if (ilqgk_launch_backpass(&h->w, &h->o, h->params, h->iter, h->stream)) return failk(h);
         h->n_launches++;
         timing_end(h, p);
@@ -1448,6 +1451,7 @@ int ilqgb_set_tuning(ilqgb_handle *h, const char *name, int value)
         if (!strcmp(name, "ls_tail_from")) h->c[i]->ls_tail_from = value;
         else if (!strcmp(name, "pass_index")) { h->c[i]->iter = value; h->c[i]->started = 1; }
         else if (!strcmp(name, "bp_latency")) h->c[i]->bp_latency = value;
+        else if (!strcmp(name, "cw_lpp") && (value == 32 || value == 16 || value == 8)) h->c[i]->cw_lpp = value;
         else { snprintf(h->err, sizeof h->err, "unknown tuning knob"); return -1; }
     }
     return 0;

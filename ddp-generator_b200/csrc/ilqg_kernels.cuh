@@ -791,6 +791,8 @@ constexpr int CW_WARPS = 4;
 #define ILQG_CW_MINBLOCKS 4   /* 128 registers: 16 warps per SM; measured best of 1/3/4/5 on the quadrotor */
 #endif
 
+template <class P> struct CoopWS;
+template <class P, int LPP> __host__ __device__ constexpr size_t coop_smem_bytes() { return sizeof(CoopWS<P>) * CW_WARPS * (32 / LPP); }
 /* leading dimensions of the kernel-private matrices are odd (NX | 1): lanes that walk a column hit distinct banks */
 template <class P> struct CoopWS {
     static constexpr int LX = P::NX | 1, LU = P::NU | 1;
@@ -811,25 +813,32 @@ __device__ __forceinline__ void tri_rc(int e, int &r, int &c)
     r = e - (c * (c + 1)) / 2;
 }
 
-template <class P, bool FULL, bool PP>
-__global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_warp(Work w, Opts o, ParamBlock<P> pb, int iter)
+template <class P, bool FULL, bool PP, int LPP>
+__global__ void __launch_bounds__(CW_WARPS * 32, (ILQG_CW_MINBLOCKS * LPP) / 32) k_backpass_warp(Work w, Opts o, ParamBlock<P> pb, int iter)
 {
+    static_assert(LPP == 32 || LPP == 16 || LPP == 8, "lanes per problem");
     constexpr int NX = P::NX, NU = P::NU, NQXX = P::NQXX, NQUU = P::NQUU, NQXU = P::NQXU;
     constexpr int LX = CoopWS<P>::LX, LU = CoopWS<P>::LU;
     static_assert(sizeof(Dense<P>) == sizeof(double) * P::DENSE_SIZE, "Dense layout must match the generator's table");
-    __shared__ CoopWS<P> ws_all[CW_WARPS];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int b = blockIdx.x * CW_WARPS + wid;
+    /* LPP lanes work on one problem, 32 / LPP problems share a warp: the per-problem scalar work (box QP, sparse FULL_DDP term
+       lists, short vectors) is issued once for all of them.  Groups never exchange data and synchronise among themselves only
+       (their control flow differs: QP iterations, failed passes). */
+    constexpr int PPW = 32 / LPP;
+    extern __shared__ double cw_smem[];
+    CoopWS<P> *ws_all = reinterpret_cast<CoopWS<P> *>(cw_smem);
+    const int lane = threadIdx.x & (LPP - 1), grp = (threadIdx.x & 31) / LPP, wid = threadIdx.x >> 5;
+    const unsigned gmask = (LPP == 32) ? 0xffffffffu : (((1u << LPP) - 1u) << (grp * LPP));
+    const int b = (blockIdx.x * CW_WARPS + wid) * PPW + grp;
     if (b >= w.B) return;
     if (w.status[b] != ST_RUNNING) return;
     ILQG_PARAMS(PP, b)
-    CoopWS<P> &ws = ws_all[wid];
+    CoopWS<P> &ws = ws_all[wid * PPW + grp];
     if (w.new_deriv[b]) {
         if (w.deriv_fail[b]) {
             if (lane == 0) finish(w, b, iter, w.bp_done[b] ? 1 : 0);
             return;
         }
-        __syncwarp();
+        __syncwarp(gmask);
         if (lane == 0) {
             w.new_deriv[b] = 0;
             w.n_dv[b] += 1;
@@ -844,21 +853,21 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
         P::consts(pv, ws.D);
         if (FULL) P::consts2(pv, ws.c2);
     }
-    for (int e = lane; e < NQXX; e += 32) {
+    for (int e = lane; e < NQXX; e += LPP) {
         int r, c;
         tri_rc(e, r, c);
         ws.tri_r[e] = (unsigned char)r;
         ws.tri_c[e] = (unsigned char)c;
     }
-    __syncwarp();
+    __syncwarp(gmask);
 
     double dV0 = 0.0, dV1 = 0.0, g_sum = 0.0;
     int n_bp = w.n_bp[b];
     bool done = false;
     while (!done) {
         n_bp++;
-        for (int e = lane; e < NX; e += 32) ws.Vx[e] = w.FD[(size_t)e * Bp + b];
-        for (int e = lane; e < NQXX; e += 32) {
+        for (int e = lane; e < NX; e += LPP) ws.Vx[e] = w.FD[(size_t)e * Bp + b];
+        for (int e = lane; e < NQXX; e += LPP) {
             const double v = w.FD[(size_t)(NX + e) * Bp + b];
             ws.VxxF[ws.tri_r[e] * LX + ws.tri_c[e]] = v;
             ws.VxxF[ws.tri_c[e] * LX + ws.tri_r[e]] = v;
@@ -870,19 +879,19 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
 #pragma unroll
         for (int i = 0; i < NU; i++) lk[i] = 0.0;
         bool failed = false;
-        constexpr int R1 = (P::NV1 + 31) / 32, R2 = (P::NV2 + 31) / 32;
+        constexpr int R1 = (P::NV1 + LPP - 1) / LPP, R2 = (P::NV2 + LPP - 1) / LPP;
         double pf1[R1], pf2[R2];
         {
             const double *rec = w.V1 + ((size_t)(T - 1) * Bp + b) * P::NV1;
 #pragma unroll
             for (int t = 0; t < R1; t++) {
-                const int j = lane + 32 * t;
+                const int j = lane + LPP * t;
                 pf1[t] = (j < P::NV1) ? rec[j] : 0.0;
             }
             const double *rec2 = w.V2 + ((size_t)(T - 1) * Bp + b) * P::NV2;
 #pragma unroll
             for (int t = 0; t < R2; t++) {
-                const int j = lane + 32 * t;
+                const int j = lane + LPP * t;
                 pf2[t] = (FULL && j < P::NV2_USED) ? rec2[j] : 0.0;
             }
         }
@@ -893,13 +902,13 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
                     the arithmetic of this step ---- */
 #pragma unroll
             for (int t = 0; t < R1; t++) {
-                const int j = lane + 32 * t;
+                const int j = lane + LPP * t;
                 if (j < P::NV1) Dd[P::v1_dst(j)] = pf1[t];
             }
             if (FULL) {
 #pragma unroll
                 for (int t = 0; t < R2; t++) {
-                    const int j = lane + 32 * t;
+                    const int j = lane + LPP * t;
                     if (j < P::NV2_USED) ws.v2[j] = pf2[t];
                 }
             }
@@ -907,49 +916,49 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
                 const double *rec = w.V1 + ((size_t)(k - 1) * Bp + b) * P::NV1;
 #pragma unroll
                 for (int t = 0; t < R1; t++) {
-                    const int j = lane + 32 * t;
+                    const int j = lane + LPP * t;
                     if (j < P::NV1) pf1[t] = rec[j];
                 }
                 if (FULL) {
                     const double *rec2 = w.V2 + ((size_t)(k - 1) * Bp + b) * P::NV2;
 #pragma unroll
                     for (int t = 0; t < R2; t++) {
-                        const int j = lane + 32 * t;
+                        const int j = lane + LPP * t;
                         if (j < P::NV2_USED) pf2[t] = rec2[j];
                     }
                 }
             }
-            __syncwarp();
+            __syncwarp(gmask);
             /* ---- phase 1: Qu, Qx, Vxx*fu, Vxx*fx (back_pass.c:80-92, matMult.c first halves) ---- */
-            for (int e = lane; e < NU; e += 32) {
+            for (int e = lane; e < NU; e += LPP) {
                 double acc = ws.D.cu[e];
 #pragma unroll
                 for (int r = 0; r < NX; r++) acc += ws.Vx[r] * ws.D.fu[r + e * NX];
                 ws.Qu[e] = acc;
             }
-            for (int e = lane; e < NX; e += 32) {
+            for (int e = lane; e < NX; e += LPP) {
                 double acc = ws.D.cx[e];
 #pragma unroll
                 for (int r = 0; r < NX; r++) acc += ws.Vx[r] * ws.D.fx[r + e * NX];
                 ws.Qx[e] = acc;
             }
-            for (int e = lane; e < NX * NU; e += 32) {
+            for (int e = lane; e < NX * NU; e += LPP) {
                 const int r = e % NX, j = e / NX;
                 double acc = 0.0;
 #pragma unroll
                 for (int s = 0; s < NX; s++) acc += ws.VxxF[r * LX + s] * ws.D.fu[s + j * NX];
                 ws.bc[r + j * LX] = acc;
             }
-            for (int e = lane; e < NX * NX; e += 32) {
+            for (int e = lane; e < NX * NX; e += LPP) {
                 const int r = e % NX, c = e / NX;
                 double acc = 0.0;
 #pragma unroll
                 for (int s = 0; s < NX; s++) acc += ws.VxxF[r * LX + s] * ws.D.fx[s + c * NX];
                 ws.ba[r + c * LX] = acc;
             }
-            __syncwarp();
+            __syncwarp(gmask);
             /* ---- phase 2: Qxu, Quu, Qxx (+ FULL_DDP terms; same lane owns the same entry in both) ---- */
-            for (int e = lane; e < NQXU; e += 32) {
+            for (int e = lane; e < NQXU; e += LPP) {
                 const int i = e % NX, j = e / NX;
                 double acc = 0.0;
 #pragma unroll
@@ -968,7 +977,7 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
                 }
                 ws.Qxu[e] = q;
             }
-            for (int e = lane; e < NQUU; e += 32) {
+            for (int e = lane; e < NQUU; e += LPP) {
                 const int r = ws.tri_r[e], c = ws.tri_c[e];
                 double acc = 0.0;
 #pragma unroll
@@ -994,7 +1003,7 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
                 ws.QuuS[r * LU + c] = q;
                 ws.QuuS[c * LU + r] = q;
             }
-            for (int e = lane; e < NQXX; e += 32) {
+            for (int e = lane; e < NQXX; e += LPP) {
                 const int r = ws.tri_r[e], c = ws.tri_c[e];
                 double acc = 0.0;
 #pragma unroll
@@ -1018,11 +1027,11 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
                 }
                 ws.Qxx[e] = q;
             }
-            __syncwarp();
+            __syncwarp(gmask);
             /* ---- regularisation (back_pass.c:134-159) ---- */
-            for (int e = lane; e < NQUU; e += 32) ws.QuuF[e] = ws.Quu[e];
-            for (int e = lane; e < NQXU; e += 32) ws.Qxu_reg[e] = ws.Qxu[e];
-            __syncwarp();
+            for (int e = lane; e < NQUU; e += LPP) ws.QuuF[e] = ws.Quu[e];
+            for (int e = lane; e < NQXU; e += LPP) ws.Qxu_reg[e] = ws.Qxu[e];
+            __syncwarp(gmask);
             if (o.regType == 2 && lane == 0) {
                 for (int j = 0; j < NU; j++)
                     for (int i = 0; i <= j; i++) {
@@ -1037,8 +1046,9 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
                         ws.Qxu_reg[i + j * NX] += acc * lambda;
                     }
             }
-            if (o.regType == 1 && lane < NU) ws.QuuF[utri(lane, lane)] += lambda;
-            __syncwarp();
+            if (o.regType == 1)
+                for (int e = lane; e < NU; e += LPP) ws.QuuF[utri(e, e)] += lambda;
+            __syncwarp(gmask);
             /* ---- box QP in every lane's registers (identical inputs -> identical results, uniform control flow) ---- */
             int clamped[NU], n_free;
             double invH[NQUU];
@@ -1072,15 +1082,15 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
             }
             if (qp < 1) {
                 double *rec = w.LL[cur] + ((size_t)k * Bp + b) * Rec<P>::RLL;   /* the failed QP's last iterate stays in t->l */
-                for (int e = lane; e < NU; e += 32) rec[e] = lk[e];
+                for (int e = lane; e < NU; e += LPP) rec[e] = lk[e];
                 failed = true;
                 break;
             }
-            __syncwarp();
+            __syncwarp(gmask);
             /* ---- gains (back_pass.c:173-201), one entry per lane; also the control-law record of step k ---- */
             {
                 double *rec = w.LL[cur] + ((size_t)k * Bp + b) * Rec<P>::RLL;
-            for (int e = lane; e < NU * NX; e += 32) {
+            for (int e = lane; e < NU * NX; e += LPP) {
                     const int i = e % NU, s = e / NU;
                     double acc = 0.0;
                     if (ws.clamped[i]) {
@@ -1102,8 +1112,8 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
                     ws.Lk[e] = acc;
                     rec[NU + e] = acc;
                 }
-                for (int e = lane; e < NU; e += 32) rec[e] = lk[e];
-                for (int e = NU + NU * NX + lane; e < Rec<P>::RLL; e += 32) rec[e] = 0.0;
+                for (int e = lane; e < NU; e += LPP) rec[e] = lk[e];
+                for (int e = NU + NU * NX + lane; e < Rec<P>::RLL; e += LPP) rec[e] = 0.0;
             }
             /* ---- expected reduction (back_pass.c:204-214), every lane keeps the same running sums ---- */
 #pragma unroll
@@ -1115,24 +1125,24 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
                 for (int j = 0; j < NU; j++) acc += lk[j] * ws.Quu[symtri(j, i)];
                 dV1 += 0.5 * lk[i] * acc;
             }
-            __syncwarp();
+            __syncwarp(gmask);
             /* ---- phase 3: Quu*l, Quu*L ---- */
-            for (int e = lane; e < NU; e += 32) {
+            for (int e = lane; e < NU; e += LPP) {
                 double acc = 0.0;
 #pragma unroll
                 for (int s = 0; s < NU; s++) acc += ws.QuuS[e * LU + s] * ws.lk[s];
                 ws.bv[e] = acc;
             }
-            for (int e = lane; e < NU * NX; e += 32) {
+            for (int e = lane; e < NU * NX; e += LPP) {
                 const int r = e % NU, c = e / NU;
                 double acc = 0.0;
 #pragma unroll
                 for (int s = 0; s < NU; s++) acc += ws.QuuS[r * LU + s] * ws.Lk[s + c * NU];
                 ws.bl[r + c * LU] = acc;
             }
-            __syncwarp();
+            __syncwarp(gmask);
             /* ---- phase 4: value function (back_pass.c:217-241) ---- */
-            for (int e = lane; e < NX; e += 32) {
+            for (int e = lane; e < NX; e += LPP) {
                 double acc = 0.0;
 #pragma unroll
                 for (int s = 0; s < NU; s++) acc += ws.Lk[s + e * NU] * ws.bv[s];
@@ -1143,7 +1153,7 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
                 for (int j = 0; j < NU; j++) v += ws.Qxu[e + j * NX] * ws.lk[j];
                 ws.Vx[e] = v;
             }
-            for (int e = lane; e < NQXX; e += 32) {
+            for (int e = lane; e < NQXX; e += LPP) {
                 const int r = ws.tri_r[e], c = ws.tri_c[e];
                 double acc = 0.0;
 #pragma unroll
@@ -1181,9 +1191,9 @@ __global__ void __launch_bounds__(CW_WARPS * 32, ILQG_CW_MINBLOCKS) k_backpass_w
                 }
                 g_sum += gmax;
             }
-            __syncwarp();
+            __syncwarp(gmask);
         }
-        __syncwarp();
+        __syncwarp(gmask);
         if (failed) {
             if (o.bp_single) break;
             raise_lambda(o, lambda, dlambda);
