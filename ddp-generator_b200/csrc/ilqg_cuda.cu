@@ -224,6 +224,14 @@ int ilqgk_launch_clamp(const ilqg_work *w, const double *params, double *xu_io, 
     return check(cudaGetLastError(), "k_clamp");
 }
 
+int ilqgk_eval_size(int mode) { return (mode >= 0 && mode <= 16) ? eval_size<P>(mode) : -1; }
+
+int ilqgk_launch_eval(const ilqg_work *w, const double *params, const double *in, double *out, int mode, int k, void *stream)
+{
+    PP_DISPATCH(w, (k_eval<P, PP><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, make_pb(params), in, out, mode, k)));
+    return check(cudaGetLastError(), "k_eval");
+}
+
 int ilqgk_has_post(void) { return (P::N_MU_R + P::N_MU_F) > 0; }
 
 int ilqgk_launch_finalize(const ilqg_work *w, int max_iter, void *stream)

@@ -811,6 +811,31 @@ static int ck_clamp_u(chunk *h, int k, const double *x, double *u)
     return 0;
 }
 
+static int ck_eval(chunk *h, int mode, int k, const double *x, const double *u, double *out)
+{
+    const size_t B = (size_t)h->B, nx = (size_t)h->d.nx, nu = (size_t)h->d.nu, no = (size_t)ilqgk_eval_size(mode);
+    size_t b;
+    double *tmp;
+    if (ilqgk_set_device(h->device)) return failk(h);
+    if (!no) return 0;
+    if (ensure_stage(h, B * (nx + nu + no))) return -1;
+    tmp = (double *)malloc(sizeof(double) * B * (nx + nu));
+    if (!tmp) return fail(h, "out of host memory");
+    for (b = 0; b < B; b++) {
+        memcpy(tmp + b * (nx + nu), x + b * nx, sizeof(double) * nx);
+        memcpy(tmp + b * (nx + nu) + nx, u + b * nu, sizeof(double) * nu);
+    }
+    if (ilqgk_h2d(h->d_stage, tmp, sizeof(double) * B * (nx + nu), h->stream) ||
+        ilqgk_launch_eval(&h->w, h->params, h->d_stage, h->d_stage + B * (nx + nu), mode, k, h->stream) ||
+        ilqgk_d2h(out, h->d_stage + B * (nx + nu), sizeof(double) * B * no, h->stream) || ilqgk_stream_sync(h->stream)) {
+        free(tmp);
+        return failk(h);
+    }
+    h->n_launches++;
+    free(tmp);
+    return 0;
+}
+
 static int ck_phase_derivs(chunk *h) { return ilqgk_set_device(h->device) ? failk(h) : launch_pass(h, 1, 0, 0); }
 static int ck_phase_backpass(chunk *h) { return ilqgk_set_device(h->device) ? failk(h) : launch_pass(h, 0, 1, 0); }
 static int ck_phase_linesearch(chunk *h) { return ilqgk_set_device(h->device) ? failk(h) : launch_pass(h, 0, 0, 1); }
@@ -1440,6 +1465,21 @@ int ilqgb_clamp_u(ilqgb_handle *h, int k, const double *x, double *u)
 }
 
 int ilqgb_dense_size(void) { return ilqgk_dense_size(); }
+
+int ilqgb_eval_size(int mode) { return ilqgk_eval_size(mode); }
+
+int ilqgb_eval(ilqgb_handle *h, int mode, int k, const double *x, const double *u, double *out)
+{
+    int i;
+    const int no = ilqgk_eval_size(mode);
+    if (no < 0) { snprintf(h->err, sizeof h->err, "no such evaluation mode"); return -1; }
+    if (k < 0 || k > h->T) { snprintf(h->err, sizeof h->err, "k out of range"); return -1; }
+    if (ilqgb_sync(h)) return -1;
+    for (i = 0; i < h->n; i++)
+        if (ck_eval(h->c[i], mode, k, x + (size_t)h->first[i] * h->d.nx, u + (size_t)h->first[i] * h->d.nu, out + (size_t)h->first[i] * no))
+            return hfail(h, h->c[i]);
+    return 0;
+}
 
 /* run-time tuning knobs (the defaults are chosen from the batch size): "ls_tail_from" (sequential line-search rounds before the
    parallel-alpha tail, >= n_alpha = all sequential), "bp_latency" (0/1: register-unconstrained back-pass build), and

@@ -1851,6 +1851,97 @@ __global__ void __launch_bounds__(BP_BLOCK) k_clamp(Work w, ParamBlock<P> pb, do
     for (int i = 0; i < P::NU; i++) io[P::NX + i] = u[i];
 }
 
+/* Single evaluation of the problem functions at one point per problem (the reference's MMex interface, iLQG_MMex.tem:81-226):
+ * in[b] = x | u, out[b][...] = the value of `mode` as a FULL column-major array (Hessians with both triangles, second-order
+ * dynamics as A(c, j, r) = d2 f_r / d c d j): 0 f, 1 L, 2 F, 3 Fx, 4 Fxx, 5 Lx, 6 Lu, 7 Lxx, 8 Luu, 9 Lxu, 10 fx, 11 fu, 12 fxx,
+ * 13 fuu, 14 fxu, 16 clamped u.  Multipliers are taken as zero and penalty weights as one (problems with folded constraints
+ * have no MMex in the reference).  One thread per problem; this is an inspection path, not a hot one. */
+template <class P> __host__ __device__ constexpr int eval_size(int mode)
+{
+    return mode == 0 ? P::NX : (mode == 1 || mode == 2) ? 1 : (mode == 3 || mode == 5) ? P::NX : (mode == 4 || mode == 7 || mode == 10) ? P::NX * P::NX
+         : mode == 6 ? P::NU : mode == 8 ? P::NU * P::NU : (mode == 9 || mode == 11) ? P::NX * P::NU : mode == 12 ? P::NX * P::NX * P::NX
+         : mode == 13 ? P::NU * P::NU * P::NX : mode == 14 ? P::NX * P::NU * P::NX : mode == 16 ? P::NU : 0;
+}
+
+template <class P, bool PP>
+__global__ void __launch_bounds__(BP_BLOCK) k_eval(Work w, ParamBlock<P> pb, const double *in, double *out, int mode, int k)
+{
+    constexpr int NX = P::NX, NU = P::NU, NQXX = P::NQXX, NQUU = P::NQUU, NQXU = P::NQXU;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= w.B) return;
+    ILQG_PARAMS(PP, b)
+    double x[NX], u[NU], mu[P::N_MU_R + P::N_MU_F + 1];
+#pragma unroll
+    for (int i = 0; i < NX; i++) x[i] = in[(size_t)b * (NX + NU) + i];
+#pragma unroll
+    for (int i = 0; i < NU; i++) u[i] = in[(size_t)b * (NX + NU) + NX + i];
+#pragma unroll
+    for (int i = 0; i < P::N_MU_R + P::N_MU_F + 1; i++) mu[i] = 0.0;
+    double *o_ = out + (size_t)b * eval_size<P>(mode);
+    const int T = w.T;
+    if (mode == 0 || mode == 1) {
+        double xn[NX], c;
+        P::step_free(x, u, pv, w.pk, k, T, 1.0, mu, xn, c);
+        if (mode == 0) {
+#pragma unroll
+            for (int i = 0; i < NX; i++) o_[i] = xn[i];
+        } else
+            o_[0] = c;
+    } else if (mode == 2) {
+        double c;
+        P::final_cost(x, pv, w.pk, T, T, 1.0, mu, c);
+        o_[0] = c;
+    } else if (mode == 3 || mode == 4) {
+        double cx[NX], cxx[NQXX];
+        P::derivs_final(x, pv, w.pk, T, T, 1.0, mu, cx, cxx);
+        if (mode == 3) {
+#pragma unroll
+            for (int i = 0; i < NX; i++) o_[i] = cx[i];
+        } else
+            for (int c = 0; c < NX; c++)
+                for (int r = 0; r < NX; r++) o_[r + c * NX] = cxx[symtri(r, c)];
+    } else if (mode == 16) {
+        double xn[NX], c;
+        P::step(x, u, pv, w.pk, k, T, 1.0, mu, xn, c);
+#pragma unroll
+        for (int i = 0; i < NU; i++) o_[i] = u[i];
+    } else if (mode >= 5 && mode <= 14) {
+        Dense<P> D;
+        double *Dd = reinterpret_cast<double *>(&D);
+        for (int i = 0; i < P::DENSE_SIZE; i++) Dd[i] = 0.0;
+        double v1[P::NV1], v2[P::NV2];
+        P::consts(pv, D);
+        P::derivs_full(x, u, pv, w.pk, k, T, 1.0, mu, v1, v2);
+        P::unpack(v1, D);
+        if (mode == 5) for (int i = 0; i < NX; i++) o_[i] = D.cx[i];
+        if (mode == 6) for (int i = 0; i < NU; i++) o_[i] = D.cu[i];
+        if (mode == 7) for (int c = 0; c < NX; c++) for (int r = 0; r < NX; r++) o_[r + c * NX] = D.cxx[symtri(r, c)];
+        if (mode == 8) for (int c = 0; c < NU; c++) for (int r = 0; r < NU; r++) o_[r + c * NU] = D.cuu[symtri(r, c)];
+        if (mode == 9) for (int i = 0; i < NQXU; i++) o_[i] = D.cxu[i];
+        if (mode == 10) for (int i = 0; i < NX * NX; i++) o_[i] = D.fx[i];
+        if (mode == 11) for (int i = 0; i < NX * NU; i++) o_[i] = D.fu[i];
+        if (mode >= 12) {
+            /* component r of the second-order dynamics = the FULL_DDP contraction with the r-th unit vector for Vx: the sparse
+               term lists then reduce to 0 + 1.0 * entry (other terms add 0 * entry = +-0) */
+            for (int r = 0; r < NX; r++) {
+                double e[NX], q[NQXX > NQXU ? NQXX : NQXU];
+                for (int i = 0; i < NX; i++) e[i] = (i == r) ? 1.0 : 0.0;
+                for (int i = 0; i < (NQXX > NQXU ? NQXX : NQXU); i++) q[i] = 0.0;
+                if (mode == 12) {
+                    P::add2_Qxx(e, v2, pv, q);
+                    for (int j = 0; j < NX; j++) for (int c = 0; c < NX; c++) o_[c + j * NX + r * NX * NX] = q[symtri(c, j)];
+                } else if (mode == 13) {
+                    P::add2_Quu(e, v2, pv, q);
+                    for (int j = 0; j < NU; j++) for (int c = 0; c < NU; c++) o_[c + j * NU + r * NU * NU] = q[symtri(c, j)];
+                } else {
+                    P::add2_Qxu(e, v2, pv, q);
+                    for (int j = 0; j < NU; j++) for (int c = 0; c < NX; c++) o_[c + j * NX + r * NX * NU] = q[c + j * NX];
+                }
+            }
+        }
+    }
+}
+
 /* after the last pass: problems still running hit the iteration limit (iLQG.c:365-377) */
 __global__ void k_finalize(Work w, int max_iter)
 {

@@ -1,11 +1,13 @@
 """python -m ilqg_gen <problem> [...] <outroot>        built-in problem modules
    python -m ilqg_gen --mac file.mac <name> <outroot>  a reference-style Maxima problem file
-writes <outroot>/<name>/{iLQG_problem.h, iLQG_func.c, <name>_device.cuh}."""
+writes <outroot>/<name>/{iLQG_problem.h, iLQG_func.c, <name>_device.cuh} and, for problems without folded constraints,
+iLQG_MMex.c (the single-evaluation gateway of iLQG_MMex.tem)."""
 import os
 import sys
 
 from .emit_c import emit_func_c, emit_problem_h
 from .emit_cuda import emit_device
+from .emit_mmex import emit_mmex_c
 from .lower import lower
 from .problems import REGISTRY
 
@@ -26,6 +28,13 @@ def generate(name, outdir, mac=None):
         f.write(emit_func_c(m))
     with open(os.path.join(outdir, f"{name}_device.cuh"), "w") as f:
         f.write(emit_device(m, "Prob" + prob.name))
+    mmex = os.path.join(outdir, "iLQG_MMex.c")
+    if any(m.n_mu.values()):      # no multiplier inputs in the MMex interface: such problems have none (iLQG_MMex.tem)
+        if os.path.exists(mmex):
+            os.remove(mmex)
+    else:
+        with open(mmex, "w") as f:
+            f.write(emit_mmex_c(m))
     return m
 
 

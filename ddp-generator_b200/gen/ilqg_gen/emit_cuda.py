@@ -155,10 +155,10 @@ def emit_device(m, struct_name) -> str:
     UNUSED = "        (void)p; (void)pk; (void)k; (void)N; (void)w_pen; (void)mu;"
 
     # ---- rollout step ----------------------------------------------------------------------------------------
-    def step_body(cost_only):
+    def step_body(cost_only, clamp=True):
         scA = Scope("a")
         aux_outs(scA, m.aux, lambda a: a.used_running and not a.dep_u)
-        if not cost_only:
+        if not cost_only and clamp:
             for rec in m.h:
                 scA.out(("var", "limit"), rec["limit"], False)
                 j, cmp_ = rec["input"], (">" if rec["sign"] > 0 else "<")
@@ -175,6 +175,11 @@ def emit_device(m, struct_name) -> str:
     o.append(f"    __device__ __forceinline__ static bool step(const double *x, double *u, {ARGS}, double *x_next, double &c) {{")
     o.append("        bool ok = true; double limit; (void)limit;\n" + UNUSED)
     o.append(step_body(False))
+    o.append("        return ok;\n    }\n")
+    o.append("    /* dynamics and cost of one timestep at the given u, NOT clamped (single evaluations: iLQG_MMex.tem mode 0) */")
+    o.append(f"    __device__ __forceinline__ static bool step_free(const double *x, const double *u, {ARGS}, double *x_next, double &c) {{")
+    o.append("        bool ok = true;\n" + UNUSED)
+    o.append(step_body(False, clamp=False))
     o.append("        return ok;\n    }\n")
     o.append(f"    __device__ __forceinline__ static bool step_cost(const double *x, const double *u, {ARGS}, double &c) {{")
     o.append("        bool ok = true;\n" + UNUSED)

@@ -103,6 +103,13 @@ int ilqgb_phase_linesearch(ilqgb_handle *h);
 int ilqgb_phase_backpass_once(ilqgb_handle *h);
 int ilqgb_phase_multipliers(ilqgb_handle *h, int init);
 int ilqgb_clamp_u(ilqgb_handle *h, int k, const double *x, double *u);
+/* single evaluations of the generated problem functions at one point per problem, the reference's MMex interface
+ * (iLQG_MMex.tem:81-226; mex/iLQG_MMex_b200.c is the gateway): x [batch][nx], u [batch][nu], 0-based step k; out
+ * [batch][ilqgb_eval_size(mode)] as FULL column-major arrays.  mode: 0 f, 1 L, 2 F, 3 Fx, 4 Fxx, 5 Lx, 6 Lu, 7 Lxx, 8 Luu, 9 Lxu,
+ * 10 fx, 11 fu, 12 fxx (nx x nx x nx: A(c,j,r) = d2 f_r / dx_c dx_j), 13 fuu (nu x nu x nx), 14 fxu (nx x nu x nx), 15 y (empty),
+ * 16 clamped u.  Multipliers are zero and penalty weights one here. */
+int ilqgb_eval_size(int mode);
+int ilqgb_eval(ilqgb_handle *h, int mode, int k, const double *x, const double *u, double *out);
 /* "dense" field of ilqgb_get: [batch][n_hor][ilqgb_dense_size()] = fx fu cx cxx cu cuu cxu lower upper lower_sign upper_sign
  * lower_hx upper_hx of every step (the derivative members of trajEl_t) as the backward pass sees them */
 int ilqgb_dense_size(void);

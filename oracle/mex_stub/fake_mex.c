@@ -160,6 +160,10 @@ void mexErrMsgIdAndTxt(const char *id, const char *fmt, ...)
     abort();
 }
 
+void mexErrMsgTxt(const char *msg) { mexErrMsgIdAndTxt("", "%s", msg); }
+
+double mxGetScalar(const mxArray *a) { return (a && a->cls == mxDOUBLE_CLASS && numel(a) > 0) ? ((const double *)a->data)[0] : 0.0; }
+
 void mexWarnMsgIdAndTxt(const char *id, const char *fmt, ...)
 {
     (void)id;

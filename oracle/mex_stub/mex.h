@@ -42,6 +42,7 @@ int mxGetNumberOfFields(const mxArray *a);
 mxArray *mxGetFieldByNumber(const mxArray *a, mwIndex index, int field);
 const char *mxGetFieldNameByNumber(const mxArray *a, int field);
 mxArray *mxGetField(const mxArray *a, mwIndex index, const char *name);
+double mxGetScalar(const mxArray *a);
 
 /* creation / memory */
 mxArray *mxCreateDoubleMatrix(mwSize m, mwSize n, mxComplexity c);
@@ -55,6 +56,7 @@ void mxFree(void *p);
 /* host interaction */
 int mexPrintf(const char *fmt, ...);
 void mexErrMsgIdAndTxt(const char *id, const char *fmt, ...); /* does not return (longjmp into fm_call) */
+void mexErrMsgTxt(const char *msg);                           /* the same without an identifier */
 void mexWarnMsgIdAndTxt(const char *id, const char *fmt, ...);
 
 /* test-side helpers (not part of the mex API) */

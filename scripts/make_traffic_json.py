@@ -17,7 +17,7 @@ out = {"source": sys.argv[3], "passes_averaged": n_pass}
 for c in ("derivs", "backpass", "linesearch"):
     ls = [l for l in sel if cls(l["k"]) == c]
     byt = sum(l["dram__bytes_read.sum"] + l["dram__bytes_write.sum"] for l in ls)
-    n_timed = sum(1 for l in ls if "k_ls_commit" not in l["k"])
+    n_timed = sum(1 for l in ls if "k_ls_commit" not in l["k"])   # tail + commit_seg + commit are one timed launch
     out[c] = {"dram_bytes_per_pass": byt / n_pass, "kernels_per_pass": len(ls) / n_pass, "bench_launches_per_pass": n_timed / n_pass,
               "dram_bytes_per_launch": byt / max(n_timed, 1), "ms_per_pass_under_ncu": sum(l["gpu__time_duration.sum"] for l in ls) / n_pass / 1e6}
 json.dump(out, open(sys.argv[2], "w"), indent=1)
