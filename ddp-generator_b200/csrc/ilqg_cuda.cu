@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include "ilqg_kernels.cuh"
+#include "mod_chol.cuh"
 #include ILQG_PROBLEM_HEADER
 #include "ilqg_cuda.h"
 
@@ -230,6 +231,32 @@ int ilqgk_launch_eval(const ilqg_work *w, const double *params, const double *in
 {
     PP_DISPATCH(w, (k_eval<P, PP><<<nblk(w->B, BP_BLOCK), BP_BLOCK, 0, (cudaStream_t)stream>>>(*w, make_pb(params), in, out, mode, k)));
     return check(cudaGetLastError(), "k_eval");
+}
+
+/* modified Cholesky of `count` packed n x n matrices (host arrays in, host arrays out), one thread per matrix */
+int ilqgk_mod_chol(int n, int count, const double *A, const double *b, double *fac, double *E, int *P, double *ret, double *inv, double *H, double *x)
+{
+    if (n < 1 || n > MC_MAXN || count < 1) { snprintf(g_err, sizeof g_err, "mod_chol: n must be 1..%d and count >= 1", MC_MAXN); return -1; }
+    const size_t np = (size_t)(n * (n + 1)) / 2, nA = np * count, nv = (size_t)n * count;
+    double *d = NULL;
+    int *dP = NULL;
+    int rc = -1;
+    if (check(cudaMalloc(&d, sizeof(double) * (4 * nA + 3 * nv + count)), "cudaMalloc") || check(cudaMalloc(&dP, sizeof(int) * nv), "cudaMalloc")) goto done;
+    {
+        double *dA = d, *dfac = dA + nA, *dinv = dfac + nA, *dH = dinv + nA, *db = dH + nA, *dE = db + nv, *dx = dE + nv, *dret = dx + nv;
+        if (check(cudaMemcpy(dA, A, sizeof(double) * nA, cudaMemcpyHostToDevice), "H2D") || check(cudaMemcpy(db, b, sizeof(double) * nv, cudaMemcpyHostToDevice), "H2D")) goto done;
+        k_mod_chol<<<nblk(count, 64), 64>>>(n, count, dA, db, dfac, dE, dP, dret, dinv, dH, dx);
+        if (check(cudaGetLastError(), "k_mod_chol") || check(cudaDeviceSynchronize(), "k_mod_chol")) goto done;
+        if (check(cudaMemcpy(fac, dfac, sizeof(double) * nA, cudaMemcpyDeviceToHost), "D2H") || check(cudaMemcpy(inv, dinv, sizeof(double) * nA, cudaMemcpyDeviceToHost), "D2H") ||
+            check(cudaMemcpy(H, dH, sizeof(double) * nA, cudaMemcpyDeviceToHost), "D2H") || check(cudaMemcpy(E, dE, sizeof(double) * nv, cudaMemcpyDeviceToHost), "D2H") ||
+            check(cudaMemcpy(x, dx, sizeof(double) * nv, cudaMemcpyDeviceToHost), "D2H") || check(cudaMemcpy(ret, dret, sizeof(double) * count, cudaMemcpyDeviceToHost), "D2H") ||
+            check(cudaMemcpy(P, dP, sizeof(int) * nv, cudaMemcpyDeviceToHost), "D2H")) goto done;
+    }
+    rc = 0;
+done:
+    cudaFree(d);
+    cudaFree(dP);
+    return rc;
 }
 
 int ilqgk_has_post(void) { return (P::N_MU_R + P::N_MU_F) > 0; }

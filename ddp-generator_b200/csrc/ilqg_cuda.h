@@ -57,6 +57,7 @@ int ilqgk_launch_dense(const ilqg_work *w, const double *params, double *out /* 
 int ilqgk_launch_clamp(const ilqg_work *w, const double *params, double *xu_io /* [B][nx+nu] */, int k, void *stream);
 int ilqgk_eval_size(int mode); /* doubles per problem mode 0..16 of ilqgk_launch_eval returns, -1 = no such mode */
 int ilqgk_launch_eval(const ilqg_work *w, const double *params, const double *in /* [B][nx+nu] */, double *out, int mode, int k, void *stream);
+int ilqgk_mod_chol(int n, int count, const double *A, const double *b, double *fac, double *E, int *P, double *ret, double *inv, double *H, double *x);
 int ilqgk_has_post(void);
 int ilqgk_launch_finalize(const ilqg_work *w, int max_iter, void *stream);
 int ilqgk_launch_count_active(const ilqg_work *w, int *d_counter, void *stream);

@@ -1466,6 +1466,14 @@ int ilqgb_clamp_u(ilqgb_handle *h, int k, const double *x, double *u)
 
 int ilqgb_dense_size(void) { return ilqgk_dense_size(); }
 
+int ilqgb_mod_chol(int device, int n, int count, const double *A, const double *b, double *factor, double *E, int *P, double *shift, double *inverse,
+                   double *H, double *x)
+{
+    if (ilqgk_device_count() < 1) { fail_create("no CUDA device available: this library has no CPU fallback"); return -1; }
+    if (ilqgk_set_device(device) || ilqgk_mod_chol(n, count, A, b, factor, E, P, shift, inverse, H, x)) { fail_create(ilqgk_last_error()); return -1; }
+    return 0;
+}
+
 int ilqgb_eval_size(int mode) { return ilqgk_eval_size(mode); }
 
 int ilqgb_eval(ilqgb_handle *h, int mode, int k, const double *x, const double *u, double *out)

@@ -110,6 +110,14 @@ int ilqgb_clamp_u(ilqgb_handle *h, int k, const double *x, double *u);
  * 16 clamped u.  Multipliers are zero and penalty weights one here. */
 int ilqgb_eval_size(int mode);
 int ilqgb_eval(ilqgb_handle *h, int mode, int k, const double *x, const double *u, double *out);
+/* The reference's modified-Cholesky family (mod_chol, mod_chol_inv, perm_tri_square, mod_chol_solve: cholesky.c:129-356) as a
+ * device unit, for `count` packed upper-triangular n x n matrices A (n <= 16) and right-hand sides b [count][n]: factor
+ * [count][n(n+1)/2], E [count][n] (diagonal shift), P [count][n] (pivot order), shift [count] (return value), inverse and H
+ * (= P L'L P', the regularised matrix) [count][n(n+1)/2], x [count][n] = (A + E)^-1 b.  Bit-identical to the reference's
+ * functions; not used by the solver (its call site in the reference, boxQP.c:69-72 under -DMOD_CHOL, is inconsistent).
+ * Errors are reported through ilqgb_last_error(NULL). */
+int ilqgb_mod_chol(int device, int n, int count, const double *A, const double *b, double *factor, double *E, int *P, double *shift,
+                   double *inverse, double *H, double *x);
 /* "dense" field of ilqgb_get: [batch][n_hor][ilqgb_dense_size()] = fx fu cx cxx cu cuu cxu lower upper lower_sign upper_sign
  * lower_hx upper_hx of every step (the derivative members of trajEl_t) as the backward pass sees them */
 int ilqgb_dense_size(void);

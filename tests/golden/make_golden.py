@@ -115,6 +115,60 @@ def make_pend():
             np.savez_compressed(os.path.join(HERE, f"pend_b{b}_ddp{ddp}.npz"), **fx)
 
 
+def modchol_cases():
+    """Inputs for the modified-Cholesky family: positive definite, indefinite, negative definite, singular and zero matrices."""
+    rng = np.random.default_rng(2468)
+    cases = []
+    for n in (1, 2, 3, 4, 6, 12):
+        for trial in range(10):
+            M = rng.standard_normal((n, n + 1))
+            A = M @ M.T
+            if trial % 5 == 1:
+                A -= (0.5 + trial) * np.eye(n)                       # indefinite
+            elif trial % 5 == 2:
+                A = -A - 0.1 * np.eye(n)                             # negative definite
+            elif trial % 5 == 3:
+                A[:, -1] = A[:, 0]; A[-1, :] = A[0, :]; A[-1, -1] = A[0, 0]   # singular (repeated row / column)
+            elif trial == 4:
+                A = np.zeros((n, n))
+            elif trial == 9:
+                A = np.diag(rng.uniform(-1, 1, n))                   # diagonal with mixed signs
+            cases.append((n, np.array([A[r, c] for c in range(n) for r in range(c + 1)]), rng.standard_normal(n)))
+    return cases
+
+
+def run_modchol(lib, n, Ap, b):
+    sym = (n * (n + 1)) // 2
+    L = Ap.copy(); E = np.zeros(n); P = np.zeros(n, np.int32); g = np.zeros(n)
+    ret = lib.mod_chol(L, n, E, P, g)
+    inv = np.zeros(sym); lib.mod_chol_inv(L, P, inv, n, np.zeros(n))
+    H = np.zeros(sym); lib.perm_tri_square(L, H, P, n)
+    x = np.zeros(n); lib.mod_chol_solve(L, P, np.ascontiguousarray(b), x, n, np.zeros(n))
+    return dict(L=L, E=E, P=P, ret=np.array([ret]), inv=inv, H=H, x=x)
+
+
+def modchol_lib(path):
+    lib = C.CDLL(path)
+    lib.mod_chol.restype = C.c_double
+    lib.mod_chol.argtypes = [_dp, C.c_int, _dp, _ip, _dp]
+    lib.mod_chol_inv.argtypes = [_dp, _ip, _dp, C.c_int, _dp]
+    lib.perm_tri_square.argtypes = [_dp, _dp, _ip, C.c_int]
+    lib.mod_chol_solve.argtypes = [_dp, _ip, _dp, _dp, C.c_int, _dp]
+    return lib
+
+
+def make_modchol():
+    """Known answers of mod_chol / mod_chol_inv / perm_tri_square / mod_chol_solve (cholesky.c:129-356), from the reference."""
+    lib = modchol_lib(oracle_lib.lib_path("reference", "car", 0))
+    out = {}
+    cases = modchol_cases()
+    for i, (n, Ap, b) in enumerate(cases):
+        r = run_modchol(lib, n, Ap, b)
+        out.update({f"c{i}_n": np.array([n]), f"c{i}_A": Ap, f"c{i}_b": b, **{f"c{i}_{k}": v for k, v in r.items()}})
+    out["count"] = np.array([len(cases)])
+    np.savez_compressed(os.path.join(HERE, "modchol_kats.npz"), **out)
+
+
 def main():
     assert oracle_lib.available("reference", "car", 0), "build oracle/_ref first (make -C oracle ref)"
     x0, u0 = W.car_single()
@@ -147,6 +201,7 @@ def main():
         fx["mult_t"] = s.get("mult_t")
         np.savez_compressed(os.path.join(HERE, f"brachi_hli_ddp{ddp}.npz"), **fx)
     make_pend()
+    make_modchol()
     np.savez_compressed(os.path.join(HERE, "kats.npz"), **kats())
     # bit patterns of the deterministic math layer on a fixed grid
     lib = C.CDLL(os.path.join(ROOT, "oracle", "_build", "libdmcheck.so"))
@@ -163,5 +218,7 @@ def main():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "pend":      # only the fixtures added in round 2 (the others stay byte-identical)
         make_pend()
+    elif len(sys.argv) > 1 and sys.argv[1] == "modchol":
+        make_modchol()
     else:
         main()
