@@ -225,7 +225,7 @@ int ilqgk_launch_clamp(const ilqg_work *w, const double *params, double *xu_io, 
     return check(cudaGetLastError(), "k_clamp");
 }
 
-int ilqgk_eval_size(int mode) { return (mode >= 0 && mode <= 16) ? eval_size<P>(mode) : -1; }
+int ilqgk_eval_size(int mode) { return (mode >= 0 && mode <= 17) ? eval_size<P>(mode) : -1; }
 
 int ilqgk_launch_eval(const ilqg_work *w, const double *params, const double *in, double *out, int mode, int k, void *stream)
 {

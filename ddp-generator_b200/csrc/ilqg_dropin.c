@@ -120,8 +120,23 @@ void printParams(double **p, int k)
         PRNT("\n");
     }
 }
-int get_g_size() { return 0; }
-int calcG(double g[], trajEl_t *t, int k, double *p[]) { (void)g; (void)t; (void)k; (void)p; return 1; }
+/* user outputs of the problem file (iLQG_func.tem:511-521), evaluated on the device like everything else; calcG has no tOptSet:
+   like clampU it takes the parameters from p (a [k]-indexed parameter is read at index k only, so any horizon >= k serves) */
+int get_g_size() { return ilqgb_eval_size(17); }
+static ilqgb_handle *cached_handle_covering(int k);
+int calcG(double g[], trajEl_t *t, int k, double *p[])
+{
+    ilqgb_handle *h;
+    int i;
+    if (ilqgb_eval_size(17) <= 0) return 1;
+    for (i = 0; i < n_params; i++)
+        if (paramdesc[i]->size == -1) return 0;   /* the length of a [k]-indexed vector is not known here */
+    h = cached_handle_covering(k);
+    if (!h) return 0;
+    for (i = 0; i < n_params; i++)
+        if (ilqgb_set_param(h, i, p[i], paramdesc[i]->size)) return 0;
+    return ilqgb_eval(h, 17, k, t->x, t->u, g) ? 0 : 1;
+}
 
 /* ---- multipliers: struct members <-> device order [equalities..., inequalities...] ----------------------------------------- */
 #define N_EL ((int)(sizeof(multipliersEl_t) / sizeof(double)))
@@ -181,6 +196,9 @@ static ilqgb_handle *handle_for(int n_hor)
     if (!g_h) PRNT("ilqg_b200: %s\n", ilqgb_last_error(NULL));
     return g_h;
 }
+
+/* any handle whose horizon reaches step k will do for a single evaluation: keep the cached one when it does */
+static ilqgb_handle *cached_handle_covering(int k) { return (g_h && g_T >= k) ? g_h : handle_for(k + 1); }
 
 static int push_params(ilqgb_handle *h, tOptSet *o)
 {

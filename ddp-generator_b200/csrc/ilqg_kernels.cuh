@@ -1854,13 +1854,13 @@ __global__ void __launch_bounds__(BP_BLOCK) k_clamp(Work w, ParamBlock<P> pb, do
 /* Single evaluation of the problem functions at one point per problem (the reference's MMex interface, iLQG_MMex.tem:81-226):
  * in[b] = x | u, out[b][...] = the value of `mode` as a FULL column-major array (Hessians with both triangles, second-order
  * dynamics as A(c, j, r) = d2 f_r / d c d j): 0 f, 1 L, 2 F, 3 Fx, 4 Fxx, 5 Lx, 6 Lu, 7 Lxx, 8 Luu, 9 Lxu, 10 fx, 11 fu, 12 fxx,
- * 13 fuu, 14 fxu, 16 clamped u.  Multipliers are taken as zero and penalty weights as one (problems with folded constraints
+ * 13 fuu, 14 fxu, 16 clamped u; 17 (not an MMex mode) the user outputs g of calcG (iLQG_func.tem:511-521).  Multipliers are taken as zero and penalty weights as one (problems with folded constraints
  * have no MMex in the reference).  One thread per problem; this is an inspection path, not a hot one. */
 template <class P> __host__ __device__ constexpr int eval_size(int mode)
 {
     return mode == 0 ? P::NX : (mode == 1 || mode == 2) ? 1 : (mode == 3 || mode == 5) ? P::NX : (mode == 4 || mode == 7 || mode == 10) ? P::NX * P::NX
          : mode == 6 ? P::NU : mode == 8 ? P::NU * P::NU : (mode == 9 || mode == 11) ? P::NX * P::NU : mode == 12 ? P::NX * P::NX * P::NX
-         : mode == 13 ? P::NU * P::NU * P::NX : mode == 14 ? P::NX * P::NU * P::NX : mode == 16 ? P::NU : 0;
+         : mode == 13 ? P::NU * P::NU * P::NX : mode == 14 ? P::NX * P::NU * P::NX : mode == 16 ? P::NU : mode == 17 ? P::NG : 0;
 }
 
 template <class P, bool PP>
@@ -1900,6 +1900,11 @@ __global__ void __launch_bounds__(BP_BLOCK) k_eval(Work w, ParamBlock<P> pb, con
         } else
             for (int c = 0; c < NX; c++)
                 for (int r = 0; r < NX; r++) o_[r + c * NX] = cxx[symtri(r, c)];
+    } else if (mode == 17) {
+        double g[P::NG + 1];
+        P::calc_g(x, u, pv, w.pk, k, T, 1.0, mu, g);
+#pragma unroll
+        for (int i = 0; i < P::NG; i++) o_[i] = g[i];
     } else if (mode == 16) {
         double xn[NX], c;
         P::step(x, u, pv, w.pk, k, T, 1.0, mu, xn, c);

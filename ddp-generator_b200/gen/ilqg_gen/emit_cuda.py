@@ -186,6 +186,17 @@ def emit_device(m, struct_name) -> str:
     o.append(step_body(True))
     o.append("        return ok;\n    }\n")
 
+    # ---- user outputs g (calcG, iLQG_func.tem:511-521) ----------------------------------------------------------------
+    scg = Scope("g")
+    aux_outs(scg, m.aux, lambda a: a.used_running)
+    for i, e in enumerate(m.g):
+        scg.out(("arr", "g", i), e, False)
+    o.append(f"    static constexpr int NG = {len(m.g)};")
+    o.append(f"    __device__ __forceinline__ static void calc_g(const double *x, const double *u, {ARGS}, double *g) {{")
+    o.append("        (void)x; (void)u; (void)g;\n" + UNUSED)
+    o.append(render(scg, NR, aux_t, guards=False) if m.g else "")
+    o.append("    }\n")
+
     # ---- final cost ------------------------------------------------------------------------------------------
     sc = Scope("f")
     aux_outs(sc, m.aux, lambda a: a.used_final)

@@ -214,6 +214,9 @@ def lower(prob: Problem, full_ddp_blocks=True) -> Model:
     m.Fcx = [entry(i, D(F, m.x[i])) for i in range(nx)]
     m.Fcxx = [entry(utri(r, c), D(F, m.x[r], m.x[c])) for c in range(nx) for r in range(c + 1)]
 
+    # ---- user outputs g (iLQG_func.tem:511-521): plain expressions of x, u, parameters and auxiliary values ----------------
+    m.g = [lower_expr(e) for e in getattr(prob, "g", [])]
+
     # ---- input constraints (genenerator_main.mac:373-447) ---------------------------------------------
     m.h = []
     for hi, hexpr in enumerate(prob.h):
@@ -277,6 +280,7 @@ def lower(prob: Problem, full_ddp_blocks=True) -> Model:
             running_roots += [e.expr for e in blk]
     for rec in m.h:
         running_roots += [rec["limit"]] + rec["hx"]
+    running_roots += list(m.g)
     for kind in ("le", "li"):
         for rec in m.mult[kind]:
             running_roots += [rec["h"]] + [rec[k] for k in ("next", "next_A", "next_I") if k in rec]

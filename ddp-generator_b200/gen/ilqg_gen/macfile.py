@@ -7,6 +7,7 @@ Understood statements (terminated by `;` or `$`, `/* ... */` comments ignored):
                                                     once per step and shared), referenced as name it is substituted
     f[state]: expr;  L: expr;  F: expr;             dynamics, running cost, final cost
     h[i]: expr;  hfe[i] / hfi[i] / hle[i] / hli[i]  input box constraints, terminal / running (in)equalities
+    g[i]: expr;                                     user outputs evaluated by calcG (iLQG_func.tem:511-521)
     fname(a, b, ...):= expr;                        helper function
     assume(sym > 0);  assume(sym < 0);              sign assumptions (used by abs / integrate)
 Expressions: + - * / ^, numbers, sqrt sin cos tan asin acos abs, integrate(e, v, a, b), expand, factor, helper calls.
@@ -23,7 +24,7 @@ from .problem import Problem
 
 _FUNCS = {"sqrt": sp.sqrt, "sin": sp.sin, "cos": sp.cos, "tan": sp.tan, "asin": sp.asin, "acos": sp.acos, "abs": sp.Abs,
           "expand": sp.expand, "factor": sp.factor, "ratsimp": sp.ratsimp}
-_SPECIAL_ARRAYS = ("f", "h", "hfe", "hfi", "hle", "hli")
+_SPECIAL_ARRAYS = ("f", "h", "hfe", "hfi", "hle", "hli", "g")
 
 
 class _ParamArray:
@@ -189,13 +190,13 @@ def load_mac(path, name=None):
         if idx not in st:
             raise ValueError("elements of f must be indexed by elements of x")
         P.f[st[idx]] = e
-    for arr in ("h", "hfe", "hfi", "hle", "hli"):
+    for arr in ("h", "hfe", "hfi", "hle", "hli", "g"):
         items = sorted(lists.get(arr, []), key=lambda t: int(t[0]))   # enforced in ascending index (README.md:36)
         setattr(P, arr, [e for _, e in items])
 
     # parameters: scalars and arrays, as found in the expressions
     allsyms = set()
-    for e in [P.L, P.F] + list(P.f.values()) + P.h + P.hfe + P.hfi + P.hle + P.hli + [a.definition for a in P.aux]:
+    for e in [P.L, P.F] + list(P.f.values()) + P.h + P.hfe + P.hfi + P.hle + P.hli + P.g + [a.definition for a in P.aux]:
         allsyms |= sp.sympify(e).free_symbols
     from .problem import ParamDesc
     for nm, sy in scalars.items():

@@ -43,6 +43,7 @@ class Problem:
         self.hfi = []
         self.hle = []
         self.hli = []
+        self.g = []           # optional user outputs g[i](x, u, p) evaluated by calcG (iLQG_func.tem:511-521)
 
     # --- symbols -------------------------------------------------------------------------------------
     def states(self, names):

@@ -27,4 +27,6 @@ def define():
     P.h = [-ua + lim[0], ua - lim[1], -ub + lim[0], ub - lim[1]]
     P.hle = [ua - ub]
     P.hfi = [thmin - th]
+    # user outputs for calcG (iLQG_func.tem:511-521; no reference example defines any): pendulum energy and net torque
+    P.g = [om**2 / 2 - gl * sp.cos(th), ua + ub]
     return P

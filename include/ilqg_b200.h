@@ -107,7 +107,8 @@ int ilqgb_clamp_u(ilqgb_handle *h, int k, const double *x, double *u);
  * (iLQG_MMex.tem:81-226; mex/iLQG_MMex_b200.c is the gateway): x [batch][nx], u [batch][nu], 0-based step k; out
  * [batch][ilqgb_eval_size(mode)] as FULL column-major arrays.  mode: 0 f, 1 L, 2 F, 3 Fx, 4 Fxx, 5 Lx, 6 Lu, 7 Lxx, 8 Luu, 9 Lxu,
  * 10 fx, 11 fu, 12 fxx (nx x nx x nx: A(c,j,r) = d2 f_r / dx_c dx_j), 13 fuu (nu x nu x nx), 14 fxu (nx x nu x nx), 15 y (empty),
- * 16 clamped u.  Multipliers are zero and penalty weights one here. */
+ * 16 clamped u; 17 (beyond MMex) the user outputs g[] of calcG (iLQG_func.tem:511-521), ilqgb_eval_size(17) = get_g_size().
+ * Multipliers are zero and penalty weights one here. */
 int ilqgb_eval_size(int mode);
 int ilqgb_eval(ilqgb_handle *h, int mode, int k, const double *x, const double *u, double *out);
 /* The reference's modified-Cholesky family (mod_chol, mod_chol_inv, perm_tri_square, mod_chol_solve: cholesky.c:129-356) as a

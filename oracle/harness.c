@@ -165,6 +165,8 @@ int h_back_pass(HSolver *s) { (void)s; return -1; }
 int h_line_search(HSolver *s, int iter) { (void)s; (void)iter; return -1; }
 int h_update_multipliers(HSolver *s, int init) { (void)s; (void)init; return -1; }
 #endif
+/* user outputs g of step k of the nominal trajectory (get_g_size / calcG, iLQG.h:87-88) */
+int h_calc_g(HSolver *s, int k, double *g) { return calcG(g, &s->o.nominal->t[k], k, s->o.p) ? get_g_size() : -1; }
 #ifndef H_NO_PHASES
 /* clampU on step k of the nominal trajectory (its state-dependent auxiliaries are those of the last forward pass) */
 void h_clamp_u(HSolver *s, int k, double *u) { clampU(u, &s->o.nominal->t[k], k, s->o.p, s->o.n_hor); }

@@ -169,3 +169,30 @@ def test_clampU_through_reference_api():
             s.close()
         assert np.array_equal(outs[0], outs[1]), problem
         assert not np.array_equal(outs[0][0], [2.0, -5.0])
+
+
+def test_user_outputs_through_reference_api():
+    """get_g_size / calcG (iLQG.h:87-88, iLQG_func.tem:511-521): the pend problem defines two outputs g[]"""
+    import ctypes as C
+    x0, u0 = W.pend_batch(1)
+    outs = []
+    for kind in (PU.oracle_kinds("pend", 0)[0], "b200"):
+        O = oracle_lib.OracleLib(kind, "pend", 0)
+        O.lib.h_calc_g.argtypes = [C.c_void_p, C.c_int, np.ctypeslib.ndpointer(dtype=np.float64)]
+        s = O.solver(W.PEND_T)
+        s.set_opts(W.PEND_OPTS); s.set_params(W.PEND_PARAMS)
+        assert s.init(x0[0], u0[0])
+        res = []
+        for k in (0, 17, W.PEND_T - 1):
+            g = np.zeros(4)
+            assert O.lib.h_calc_g(s.h, k, g) == 2
+            res.append(g[:2].copy())
+        outs.append(np.stack(res))
+        s.close()
+    assert np.array_equal(outs[0], outs[1]) and np.abs(outs[0]).min() > 0
+    c = oracle_lib.OracleLib("b200", "car", 0)
+    c.lib.h_calc_g.argtypes = [C.c_void_p, C.c_int, np.ctypeslib.ndpointer(dtype=np.float64)]
+    sc = c.solver(10); sc.set_params(W.CAR_PARAMS)
+    xc, uc = W.car_batch(1, T=10)
+    assert sc.init(xc[0], uc[0]) and c.lib.h_calc_g(sc.h, 3, np.zeros(2)) == 0       # a problem without outputs: size 0
+    sc.close()
