@@ -219,9 +219,9 @@ IDLE_S = 1.5
 def algorithmic_bytes(nx, nu, nv, T):
     """Bytes per problem and unit of work, two conventions.  `alg` = SURVEY.md 8(d): only the doubles the algorithm needs (car:
     derivative sweep 192 B/step, back pass 240 B/step, stored rollout 176 B/step, parallel-alpha tail 128 B/step).  `rec` = what
-    the kernels address: records rounded up to 32-byte sectors (car: 208 / 256 / 224 / 160 B per step)."""
+    the kernels address: x|u and L records rounded up to 32-byte sectors, l to 16 bytes (car: 208 / 240 / 208 / 144 B per step)."""
     nq = nx * (nx + 1) // 2
-    rxu, rll = 8 * ((nx + nu + 3) // 4) * 4, 8 * ((nu + nu * nx + 3) // 4) * 4
+    rxu, rll = 8 * ((nx + nu + 3) // 4) * 4, 8 * ((nu * nx + 3) // 4) * 4 + 8 * ((nu + 1) // 2) * 2     # x|u record; L record + l record
     xu, ll = 8 * (nx + nu), 8 * (nu + nu * nx)
     fin = 8 * (nx + nq)
     return {

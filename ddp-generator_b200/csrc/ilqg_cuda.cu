@@ -44,7 +44,7 @@ void ilqgk_dims(ilqgk_dims_t *d)
     d->nv1 = P::NV1; d->nv2 = P::NV2; d->npf = P::NPF_USED; d->nkp = P::NKP;
     d->n_mu_r = P::N_MU_R; d->n_mu_f = P::N_MU_F; d->n_mu_le = P::N_MU_LE; d->n_mu_fe = P::N_MU_FE;
     d->full_ddp = FULL_DDP; d->has_hx = P::HAS_HX ? 1 : 0;
-    d->rxu = Rec<P>::RXU; d->rll = Rec<P>::RLL; d->coop = use_coop<P>() ? 1 : 0;
+    d->rxu = Rec<P>::RXU; d->rlm = Rec<P>::RLM; d->rls = Rec<P>::RLS; d->coop = use_coop<P>() ? 1 : 0;
 }
 const char *ilqgk_problem_name(void) { return P::name(); }
 int ilqgk_param_count(void) { return P::param_count(); }

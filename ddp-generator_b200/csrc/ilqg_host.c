@@ -395,7 +395,10 @@ static chunk *ck_create(int device, int batch, int n_hor, int flags, void *strea
             ilqgk_memset(w->XU[i], 0, sizeof(double) * (T + 1) * Bp * d->rxu, h->stream);
         }
         DALLOC(w->x0, double, d->nx * Bp);
-        for (i = 0; i < 2; i++) DALLOC(w->LL[i], double, T * Bp * d->rll);
+        for (i = 0; i < 2; i++) {
+            DALLOC(w->LL[i], double, T * Bp * d->rlm);
+            DALLOC(w->Ll[i], double, T * Bp * d->rls);
+        }
         DALLOC(w->V1, double, T * d->nv1 * Bp);
         DALLOC(w->V2, double, d->full_ddp ? T * d->nv2 * Bp : 1);
         DALLOC(w->FD, double, (d->nx + d->nqxx) * Bp);
@@ -681,7 +684,9 @@ static int ck_start(chunk *h)
     if (h->flags & ILQGB_TRACE) { /* parity mode: control-law records start from zero like a calloc'ed trajectory */
         int i;
         for (i = 0; i < 2; i++)
-            if (ilqgk_memset(h->w.LL[i], 0, sizeof(double) * (size_t)h->T * h->Bp * h->d.rll, h->stream)) return failk(h);
+            if (ilqgk_memset(h->w.LL[i], 0, sizeof(double) * (size_t)h->T * h->Bp * h->d.rlm, h->stream) ||
+                ilqgk_memset(h->w.Ll[i], 0, sizeof(double) * (size_t)h->T * h->Bp * h->d.rls, h->stream))
+                return failk(h);
     }
     if (ilqgk_launch_init(&h->w, &h->o, h->params, 7, h->stream)) return failk(h);
     h->n_launches++;
@@ -871,8 +876,8 @@ static int find_field(chunk *h, const char *f, field_t *o)
     else if (!strcmp(f, "x_cand")) { o->src = w->XU[1]; o->alt = w->XU[0]; o->sel = w->cur; o->n_k = h->T + 1; o->n_i = d->nx; o->L = lay_rec(h, d->rxu, 0); }
     else if (!strcmp(f, "u_cand")) { o->src = w->XU[1]; o->alt = w->XU[0]; o->sel = w->cur; o->n_k = h->T; o->n_i = d->nu; o->L = lay_rec(h, d->rxu, d->nx); }
     else if (!strcmp(f, "x0")) { o->src = w->x0; o->n_k = 1; o->n_i = d->nx; o->L = lay_soa(h, d->nx); }
-    else if (!strcmp(f, "l")) { o->src = w->LL[0]; o->alt = w->LL[1]; o->sel = w->cur; o->n_k = h->T; o->n_i = d->nu; o->L = lay_rec(h, d->rll, 0); }
-    else if (!strcmp(f, "L")) { o->src = w->LL[0]; o->alt = w->LL[1]; o->sel = w->cur; o->n_k = h->T; o->n_i = d->nu * d->nx; o->L = lay_rec(h, d->rll, d->nu); }
+    else if (!strcmp(f, "l")) { o->src = w->Ll[0]; o->alt = w->Ll[1]; o->sel = w->cur; o->n_k = h->T; o->n_i = d->nu; o->L = lay_rec(h, d->rls, 0); }
+    else if (!strcmp(f, "L")) { o->src = w->LL[0]; o->alt = w->LL[1]; o->sel = w->cur; o->n_k = h->T; o->n_i = d->nu * d->nx; o->L = lay_rec(h, d->rlm, 0); }
     else if (!strcmp(f, "v1")) { o->src = w->V1; o->n_k = h->T; o->n_i = d->nv1; o->L = d->coop ? lay_rec(h, d->nv1, 0) : lay_soa(h, o->n_i); }
     else if (!strcmp(f, "v2") && d->full_ddp) { o->src = w->V2; o->n_k = h->T; o->n_i = d->nv2; o->L = d->coop ? lay_rec(h, d->nv2, 0) : lay_soa(h, o->n_i); }
     else if (!strcmp(f, "fd")) { o->src = w->FD; o->n_k = 1; o->n_i = d->nx + d->nqxx; o->L = lay_soa(h, o->n_i); }

@@ -335,12 +335,16 @@ __device__ __forceinline__ int box_qp(const double *H, const double *g, const do
 
 /* ---- per-(step, problem) records in HBM ---------------------------------------------------------------------------
  * The data a rollout reads and writes is stored as one small contiguous record per (timestep, problem):
- *   XU[buf][k][b][RXU] = x (NX) | u (NU) | pad        LL[k][b][RLL] = l (NU) | L (NU*NX) | pad
- * with record sizes rounded up to 32-byte sectors.  Any lane -> problem mapping (the line search works on compacted
+ *   XU[buf][k][b][RXU] = x (NX) | u (NU) | pad        LL[buf][k][b][RLM] = L (NU*NX) | pad        Ll[buf][k][b][RLS] = l (NU) | pad
+ * with the x|u and L records rounded up to 32-byte sectors and the small l record to 16 bytes (two problems per sector).  The
+ * gains and the feed-forward term are separate arrays since round 2: DRAM is fetched in 64-byte granules, a 96-byte l|L record
+ * of a problem whose neighbours are not in the (compacted) list cost 2-3 granules for 80 useful bytes (round 1 measured 239 B
+ * read per step in round 1 of the line search against 160 B in round 0); a 64-byte L record is exactly one granule.  Any lane -> problem mapping (the line search works on compacted
  * problem lists) then moves only fully used sectors, and a warp with lane == problem still reads one contiguous run. */
 template <class P> struct Rec {
     static constexpr int RXU = ((P::NX + P::NU + 3) / 4) * 4;
-    static constexpr int RLL = ((P::NU + P::NU * P::NX + 3) / 4) * 4;
+    static constexpr int RLM = ((P::NU * P::NX + 3) / 4) * 4;   /* gains L */
+    static constexpr int RLS = ((P::NU + 1) / 2) * 2;            /* feed-forward l */
 };
 
 template <int N> __device__ __forceinline__ void ld_rec(const double *p, double *out)
@@ -653,7 +657,7 @@ __global__ void __launch_bounds__(BP_BLOCK, MINB) k_backpass(Work w, Opts o, Par
             if (qp < 1) {
                 /* the reference's boxQP iterates on t->l in place (back_pass.c:163-171): a failed QP leaves its last iterate
                    in the trajectory, which is what a solve that ends on this failure returns */
-                double *rec = w.LL[cur] + ((size_t)k * Bp + b) * Rec<P>::RLL;
+                double *rec = w.Ll[cur] + ((size_t)k * Bp + b) * Rec<P>::RLS;
 #pragma unroll
                 for (int i = 0; i < NU; i++) rec[i] = lk[i];
                 failed = true;
@@ -694,15 +698,14 @@ __global__ void __launch_bounds__(BP_BLOCK, MINB) k_backpass(Work w, Opts o, Par
                 }
             }
             {
-                constexpr int RLL = Rec<P>::RLL;
-                double rec[RLL];
+                constexpr int RLM = Rec<P>::RLM, RLS = Rec<P>::RLS;
+                double recL[RLM], recl[RLS];
 #pragma unroll
-                for (int i = 0; i < NU; i++) rec[i] = lk[i];
+                for (int i = 0; i < RLS; i++) recl[i] = (i < NU) ? lk[i] : 0.0;
 #pragma unroll
-                for (int i = 0; i < NU * NX; i++) rec[NU + i] = Lk[i];
-#pragma unroll
-                for (int i = NU + NU * NX; i < RLL; i++) rec[i] = 0.0;
-                st_rec<RLL>(w.LL[cur] + ((size_t)k * Bp + b) * RLL, rec);
+                for (int i = 0; i < RLM; i++) recL[i] = (i < NU * NX) ? Lk[i] : 0.0;
+                st_rec<RLM>(w.LL[cur] + ((size_t)k * Bp + b) * RLM, recL);
+                st_rec<RLS>(w.Ll[cur] + ((size_t)k * Bp + b) * RLS, recl);
             }
             /* expected reduction (back_pass.c:204-214) */
 #pragma unroll
@@ -1081,7 +1084,7 @@ __global__ void __launch_bounds__(CW_WARPS * 32, (ILQG_CW_MINBLOCKS * LPP) / 32)
                 for (int i = 0; i < NQUU; i++) ws.invH[i] = invH[i];
             }
             if (qp < 1) {
-                double *rec = w.LL[cur] + ((size_t)k * Bp + b) * Rec<P>::RLL;   /* the failed QP's last iterate stays in t->l */
+                double *rec = w.Ll[cur] + ((size_t)k * Bp + b) * Rec<P>::RLS;   /* the failed QP's last iterate stays in t->l */
                 for (int e = lane; e < NU; e += LPP) rec[e] = lk[e];
                 failed = true;
                 break;
@@ -1089,7 +1092,7 @@ __global__ void __launch_bounds__(CW_WARPS * 32, (ILQG_CW_MINBLOCKS * LPP) / 32)
             __syncwarp(gmask);
             /* ---- gains (back_pass.c:173-201), one entry per lane; also the control-law record of step k ---- */
             {
-                double *rec = w.LL[cur] + ((size_t)k * Bp + b) * Rec<P>::RLL;
+                double *rec = w.LL[cur] + ((size_t)k * Bp + b) * Rec<P>::RLM, *recl = w.Ll[cur] + ((size_t)k * Bp + b) * Rec<P>::RLS;
             for (int e = lane; e < NU * NX; e += LPP) {
                     const int i = e % NU, s = e / NU;
                     double acc = 0.0;
@@ -1110,10 +1113,10 @@ __global__ void __launch_bounds__(CW_WARPS * 32, (ILQG_CW_MINBLOCKS * LPP) / 32)
                         }
                     }
                     ws.Lk[e] = acc;
-                    rec[NU + e] = acc;
+                    rec[e] = acc;
                 }
-                for (int e = lane; e < NU; e += LPP) rec[e] = lk[e];
-                for (int e = NU + NU * NX + lane; e < Rec<P>::RLL; e += LPP) rec[e] = 0.0;
+                for (int e = NU * NX + lane; e < Rec<P>::RLM; e += LPP) rec[e] = 0.0;
+                for (int e = lane; e < Rec<P>::RLS; e += LPP) recl[e] = (e < NU) ? lk[e] : 0.0;
             }
             /* ---- expected reduction (back_pass.c:204-214), every lane keeps the same running sums ---- */
 #pragma unroll
@@ -1236,7 +1239,7 @@ template <class P, bool STORE = true, bool CKPT = false>
 __device__ __forceinline__ bool rollout(const Work &w, const double *pv, int b, int from, int to, double alpha,
                                         double w_pen_l, double w_pen_f, double &csum, double *ckpt = nullptr)
 {
-    constexpr int NX = P::NX, NU = P::NU, RXU = Rec<P>::RXU, RLL = Rec<P>::RLL;
+    constexpr int NX = P::NX, NU = P::NU, RXU = Rec<P>::RXU, RLM = Rec<P>::RLM, RLS = Rec<P>::RLS, RLL = NU + RLM;
     const size_t Bp = w.Bp;
     const int T = w.T;
     double xu[RXU], xn[NX], mu[P::N_MU_R + P::N_MU_F + 1];
@@ -1252,7 +1255,10 @@ __device__ __forceinline__ bool rollout(const Work &w, const double *pv, int b, 
     double nom[RXU], ll[RLL], nom_n[PF ? RXU : 1], ll_n[PF ? RLL : 1];
     if (PF) {
         ld_rec<NX + NU>(w.XU[from] + (size_t)b * RXU, nom);
-        if (alpha != 0.0) ld_rec<NU + NU * NX>(w.LL[from] + (size_t)b * RLL, ll);
+        if (alpha != 0.0) {
+            ld_rec<NU>(w.Ll[from] + (size_t)b * RLS, ll);
+            ld_rec<NU * NX>(w.LL[from] + (size_t)b * RLM, ll + NU);
+        }
     }
     const int seg_len = ls_seg_len(T);
     int next_ck = 0;
@@ -1266,11 +1272,17 @@ __device__ __forceinline__ bool rollout(const Work &w, const double *pv, int b, 
         if (PF) {
             if (k + 1 < T) {
                 ld_rec<PF ? NX + NU : 1>(w.XU[from] + ((size_t)(k + 1) * Bp + b) * RXU, nom_n);
-                if (alpha != 0.0) ld_rec<PF ? NU + NU * NX : 1>(w.LL[from] + ((size_t)(k + 1) * Bp + b) * RLL, ll_n);
+                if (alpha != 0.0) {
+                    ld_rec<PF ? NU : 1>(w.Ll[from] + ((size_t)(k + 1) * Bp + b) * RLS, ll_n);
+                    ld_rec<PF ? NU * NX : 1>(w.LL[from] + ((size_t)(k + 1) * Bp + b) * RLM, ll_n + (PF ? NU : 0));
+                }
             }
         } else {
             ld_rec<NX + NU>(w.XU[from] + ((size_t)k * Bp + b) * RXU, nom);
-            if (alpha != 0.0) ld_rec<NU + NU * NX>(w.LL[from] + ((size_t)k * Bp + b) * RLL, ll);
+            if (alpha != 0.0) {
+                ld_rec<NU>(w.Ll[from] + ((size_t)k * Bp + b) * RLS, ll);
+                ld_rec<NU * NX>(w.LL[from] + ((size_t)k * Bp + b) * RLM, ll + NU);
+            }
         }
         if (alpha != 0.0) {
 #pragma unroll
@@ -1347,7 +1359,7 @@ template <class P>
 __device__ __forceinline__ void rollout_segment(const Work &w, const double *pv, int b, int from, int to, double alpha,
                                                 double w_pen_l, int k0, int k1, const double *xs)
 {
-    constexpr int NX = P::NX, NU = P::NU, RXU = Rec<P>::RXU, RLL = Rec<P>::RLL;
+    constexpr int NX = P::NX, NU = P::NU, RXU = Rec<P>::RXU, RLM = Rec<P>::RLM, RLS = Rec<P>::RLS, RLL = NU + RLM;
     const size_t Bp = w.Bp;
     const int T = w.T;
     double xu[RXU], xn[NX], mu[P::N_MU_R + P::N_MU_F + 1], nom[RXU], ll[RLL];
@@ -1359,7 +1371,8 @@ __device__ __forceinline__ void rollout_segment(const Work &w, const double *pv,
     for (int k = k0; k < k1; k++) {
         ld_rec<NX + NU>(w.XU[from] + ((size_t)k * Bp + b) * RXU, nom);
         if (alpha != 0.0) {
-            ld_rec<NU + NU * NX>(w.LL[from] + ((size_t)k * Bp + b) * RLL, ll);
+            ld_rec<NU>(w.Ll[from] + ((size_t)k * Bp + b) * RLS, ll);
+            ld_rec<NU * NX>(w.LL[from] + ((size_t)k * Bp + b) * RLM, ll + NU);
 #pragma unroll
             for (int j = 0; j < NU; j++) u[j] = nom[NX + j] + ll[j] * alpha;
 #pragma unroll

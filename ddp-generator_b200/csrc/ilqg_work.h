@@ -27,7 +27,8 @@ typedef struct ilqg_work {
     int B, Bp, T;
     double *XU[2];             /* two trajectory buffers of records [T+1][Bp][RXU] = x|u|pad; cur[b] says which is nominal */
     double *x0;                /* [NX][Bp] */
-    double *LL[2];             /* control-law records [T][Bp][RLL] = l | L | pad, one per trajectory buffer: like the
+    double *Ll[2];             /* feed-forward records [T][Bp][RLS] = l | pad, one per trajectory buffer like LL */
+    double *LL[2];             /* gain records [T][Bp][RLM] = L | pad, one per trajectory buffer: like the
                                   reference, where l and L are members of the trajectory element (iLQG_problem.tem:33-34) */
     double *V1, *V2, *FD;      /* time-varying derivative entries [T][NV1][Bp], [T][NV2][Bp]; final cx,cxx [NX+NQXX][Bp] */
     double *muR, *lastR, *muF, *lastF;
