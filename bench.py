@@ -15,9 +15,9 @@ the device time of the K timed steps incl. the initial rollout), inputs resident
 over the time of ONE call of the public C ABI's end-to-end entry (ilqgb_solve_host): upload (pinned host -> HBM) + solve +
 download of x, u, cost, iterations (HBM -> pinned host), pipelined per chunk stream.  The iteration count follows SURVEY.md 8d: loop passes that reached line_search.
 
-Both timed legs start from the same power state (1.5 s idle before each, stated in config.timing): a B200 runs into its
-1000 W cap within about half a second of this workload, so a leg timed right behind another one would be measured at lower
-clocks.  The end-to-end entry is warmed up once (it allocates its staging buffers on first use), like the resident path.
+Both timed legs directly follow a warm-up solve of W passes through the same entry point (stated in config.timing), so both
+start with the clocks up and the staging buffers of the end-to-end path allocated.  (An idle gap in front of a leg was tried
+and dropped: the clocks of an idle B200 take long enough to come back up that a 0.12 s leg -- the 8-GPU share -- lost 10 %.)
 
 `extra` (N = 1 only) holds the other BASELINE configs with the same fields in short form: config 3 (car, B = 4096), config 5
 (synthetic quadrotor n = 12, m = 4, T = 1000, FULL_DDP = 1, B = 16384; fp64-issue roofline of k_backpass_warp) and config 4 at
@@ -210,7 +210,8 @@ def workload_config(args):
                         f"(BASELINE config 4), max_iter={args.steps}, default options",
             "batch": args.batch, "horizon": T_HOR, "max_iter": args.steps, "sharding": "contiguous blocks of batch/N problems per GPU",
             "l2": "working set (>=160 KB per problem, tens of GB per GPU) is far larger than the 126 MB L2",
-            "timing": f"{IDLE_S} s idle before each timed leg (resident, end to end, kernels alone): same power state for all"}
+            "timing": "each timed leg (resident, end to end) directly follows a warm-up solve of W passes through the same entry point; "
+                      f"the kernels-alone leg starts after {IDLE_S} s of idle like the burst measurement of the HBM peak it is compared with"}
 
 
 IDLE_S = 1.5
@@ -326,9 +327,12 @@ def short_config(tag, problem, ddp, B, T, params, inputs, max_iter, sample_n, de
     S.solve_host_ptr(x0_t.data_ptr(), u0_t.data_ptr(), xo.data_ptr(), uo.data_ptr(), co.data_ptr(), io.data_ptr(), ro.data_ptr(), no.data_ptr())
     S.set_options({"max_iter": max_iter})
     S.upload_ptr(x0_t.data_ptr(), u0_t.data_ptr())
+    S.set_options({"max_iter": 3})
+    S.run()
+    S.set_options({"max_iter": max_iter})
+    S.upload_ptr(x0_t.data_ptr(), u0_t.data_ptr())
     l0 = S.launch_count()
     torch.cuda.synchronize()
-    time.sleep(IDLE_S)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall = time.perf_counter()
     e0.record()
@@ -342,7 +346,9 @@ def short_config(tag, problem, ddp, B, T, params, inputs, max_iter, sample_n, de
     S.download_ptr(None, None, co.data_ptr(), io.data_ptr(), ro.data_ptr(), no.data_ptr())
     n_ls = int(no.numpy().sum())
     cost_res = co.numpy().copy()
-    time.sleep(IDLE_S)
+    S.set_options({"max_iter": 3})
+    S.solve_host_ptr(x0_t.data_ptr(), u0_t.data_ptr(), xo.data_ptr(), uo.data_ptr(), co.data_ptr(), io.data_ptr(), ro.data_ptr(), no.data_ptr())
+    S.set_options({"max_iter": max_iter})
     t0 = time.perf_counter()
     S.solve_host_ptr(x0_t.data_ptr(), u0_t.data_ptr(), xo.data_ptr(), uo.data_ptr(), co.data_ptr(), io.data_ptr(), ro.data_ptr(), no.data_ptr())
     torch.cuda.synchronize()
@@ -456,17 +462,16 @@ def main():
 
     # ---- warm-up: W passes on the same inputs, through both entry points ------------------------------------------------------
     S.set_options({"max_iter": args.warmup})
+    S.solve_host_ptr(*host_ptrs)          # also allocates the staging buffers of the end-to-end path
     S.upload_ptr(x0_t.data_ptr(), u0_t.data_ptr())
     S.run()
     S.sync()
-    S.solve_host_ptr(*host_ptrs)
 
     # ---- timed region 1: inputs resident, K passes ---------------------------------------------------------------------------
     S.set_options({"max_iter": args.steps})
     S.upload_ptr(x0_t.data_ptr(), u0_t.data_ptr())
     S.sync()
     launches0 = S.launch_count()
-    time.sleep(IDLE_S)
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
@@ -475,8 +480,9 @@ def main():
     e0.record()
     S.run()
     e1.record()
-    barrier()
+    S.sync()                                  # this rank's own work (all its devices) ...
     t_wall = time.perf_counter() - t_wall
+    barrier()                                 # ... then everybody's
     clocks = sampler.stop()
     ms_dev = e0.elapsed_time(e1)
     if not (0.8 * t_wall * 1e3 <= ms_dev <= 1.02 * t_wall * 1e3):   # the events must bracket the work the host waited for
@@ -490,8 +496,10 @@ def main():
     its_total = reduce(n_ls, dist.ReduceOp.SUM if world > 1 else None)
     value = its_total / (ms_max * 1e-3)
 
-    # ---- timed region 2: end to end through the C ABI with host buffers ------------------------------------------------
-    time.sleep(IDLE_S)
+    # ---- timed region 2: end to end through the C ABI with host buffers (preceded, like region 1, by W warm-up passes) --------
+    S.set_options({"max_iter": args.warmup})
+    S.solve_host_ptr(*host_ptrs)
+    S.set_options({"max_iter": args.steps})
     esampler = ClockSampler(local_rank)
     esampler.start()
     barrier()
