@@ -82,6 +82,8 @@ class ClockSampler:
         self.lines = []
 
     def start(self):
+        if os.environ.get("BENCH_NO_SAMPLER"):      # development aid: measure the poller's own influence
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
