@@ -34,6 +34,25 @@ static ParamBlock<P> make_pb(const double *params)
     return pb;
 }
 
+/* the small-batch backward pass exists for FULL_DDP = 0 problems without state-dependent input limits; the launcher is a class
+   template so that the kernel is only instantiated where it applies */
+constexpr bool SPLIT_OK = (FULL_DDP == 0) && split_supported<P>();
+template <class Q, bool PP, bool OK> struct split_launcher {
+    static void go(const ilqg_work *, const ilqg_opts *, const double *, int, void *) {}
+};
+template <class Q, bool PP> struct split_launcher<Q, PP, true> {
+    static void go(const ilqg_work *w, const ilqg_opts *o, const double *params, int iter, void *stream)
+    {
+        constexpr size_t ssm = split_smem_bytes<Q, 4>();
+        static_assert(ssm <= 48 * 1024, "k_backpass_split: workspace exceeds the default shared-memory limit");
+        ParamBlock<Q> pb;
+        memset(&pb, 0, sizeof pb);
+        memcpy(pb.v, params, sizeof(double) * Q::NPF_USED);
+        const int ppw = o->bp_ppw < SP_BLOCK / 4 ? (o->bp_ppw < 1 ? 1 : o->bp_ppw) : SP_BLOCK / 4;
+        k_backpass_split<Q, PP, 4><<<(unsigned)((w->B + ppw - 1) / ppw), SP_BLOCK, ssm, (cudaStream_t)stream>>>(*w, *o, pb, iter);
+    }
+};
+
 extern "C" {
 
 const char *ilqgk_last_error(void) { return g_err; }
@@ -44,6 +63,7 @@ void ilqgk_dims(ilqgk_dims_t *d)
     d->nv1 = P::NV1; d->nv2 = P::NV2; d->npf = P::NPF_USED; d->nkp = P::NKP;
     d->n_mu_r = P::N_MU_R; d->n_mu_f = P::N_MU_F; d->n_mu_le = P::N_MU_LE; d->n_mu_fe = P::N_MU_FE;
     d->full_ddp = FULL_DDP; d->has_hx = P::HAS_HX ? 1 : 0;
+    d->bp_split_ok = SPLIT_OK ? 1 : 0;
     d->rxu = Rec<P>::RXU; d->rlm = Rec<P>::RLM; d->rls = Rec<P>::RLS; d->coop = use_coop<P>() ? 1 : 0;
 }
 const char *ilqgk_problem_name(void) { return P::name(); }
@@ -154,10 +174,17 @@ int ilqgk_launch_backpass(const ilqg_work *w, const ilqg_opts *o, const double *
             if (check(cudaFuncSetAttribute(k_backpass<P, FULL_DDP != 0, ILQG_BP_MINBLOCKS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return -1;
             if (dev >= 0 && dev < ILQGK_MAX_DEVICES) configured[dev] = 1;
         }
+        if (SPLIT_OK && o->bp_split == 4) {
+            PP_DISPATCH(w, (split_launcher<P, PP, SPLIT_OK>::go(w, o, params, iter, stream)));
+            return check(cudaGetLastError(), "k_backpass_split");
+        }
+        const int ppw = (o->bp_ppw >= 1 && o->bp_ppw <= 32) ? o->bp_ppw : 32;
+        const unsigned grid = nblk(w->B, ppw * (BP_BLOCK / 32));
+        if (ppw != o->bp_ppw) { snprintf(g_err, sizeof g_err, "k_backpass: problems per warp must be 1..32"); return -1; }
         if (o->bp_latency_build)
-            PP_DISPATCH(w, (k_backpass<P, FULL_DDP != 0, 1, PP><<<nblk(w->B, BP_BLOCK), BP_BLOCK, smem, (cudaStream_t)stream>>>(*w, *o, make_pb(params), iter)));
+            PP_DISPATCH(w, (k_backpass<P, FULL_DDP != 0, 1, PP><<<grid, BP_BLOCK, smem, (cudaStream_t)stream>>>(*w, *o, make_pb(params), iter)));
         else
-            PP_DISPATCH(w, (k_backpass<P, FULL_DDP != 0, ILQG_BP_MINBLOCKS, PP><<<nblk(w->B, BP_BLOCK), BP_BLOCK, smem, (cudaStream_t)stream>>>(*w, *o, make_pb(params), iter)));
+            PP_DISPATCH(w, (k_backpass<P, FULL_DDP != 0, ILQG_BP_MINBLOCKS, PP><<<grid, BP_BLOCK, smem, (cudaStream_t)stream>>>(*w, *o, make_pb(params), iter)));
     }
     return check(cudaGetLastError(), "k_backpass");
 }

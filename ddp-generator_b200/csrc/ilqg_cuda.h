@@ -9,7 +9,7 @@ extern "C" {
 #endif
 
 typedef struct ilqgk_dims_t {
-    int nx, nu, nqxx, nquu, nqxu, nv1, nv2, npf, nkp, n_mu_r, n_mu_f, n_mu_le, n_mu_fe, full_ddp, has_hx, rxu, rlm, rls, coop;
+    int nx, nu, nqxx, nquu, nqxu, nv1, nv2, npf, nkp, n_mu_r, n_mu_f, n_mu_le, n_mu_fe, full_ddp, has_hx, rxu, rlm, rls, coop, bp_split_ok;
 } ilqgk_dims_t;
 
 const char *ilqgk_last_error(void);

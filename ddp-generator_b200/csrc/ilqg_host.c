@@ -50,6 +50,8 @@ struct chunk {
     int gate_recorded;
     int ls_tail_from;      /* -1 = choose by batch size */
     int bp_latency;        /* -1 = choose by batch size */
+    int bp_ppw;            /* backward pass: problems per warp, -1 = choose by batch size */
+    int bp_split;          /* lanes per problem of the small-batch backward pass (0 = lane per problem, 4), -1 = choose by batch size */
     int cw_lpp;            /* warp-cooperative backward pass: lanes per problem */
     int total_B;           /* problems of the whole handle (all chunks run concurrently on one GPU) */
     int started;
@@ -78,6 +80,10 @@ static int fail(chunk *h, const char *msg)
 }
 
 static int failk(chunk *h) { return fail(h, ilqgk_last_error()); }
+
+#define BP_SPLIT_MAX_B 6144    /* problems on one GPU up to which the backward pass runs four lanes per problem, four problems per
+                                  warp (measured on B200, scripts/gpu_probe_split.sh, car, 50 passes, ms per backward pass: 4096 problems
+                                  2.38 one lane per problem, 1.89 the same with 8 problems per warp, 1.82 split; 16 384: 2.44 / 3.9) */
 
 static int env_int(const char *name, int dflt)
 {
@@ -360,6 +366,8 @@ static chunk *ck_create(int device, int batch, int n_hor, int flags, void *strea
     h->ls_tail_from = getenv("ILQG_LS_TAIL_FROM") ? atoi(getenv("ILQG_LS_TAIL_FROM")) : -1;
     h->bp_latency = getenv("ILQG_BP_LATENCY") ? atoi(getenv("ILQG_BP_LATENCY")) : -1;
     h->cw_lpp = env_int("ILQG_CW_LPP", 32);
+    h->bp_split = env_int("ILQG_BP_SPLIT", -1);
+    h->bp_ppw = env_int("ILQG_BP_PPW", -1);
     ilqgk_dims(&h->d);
     if (h->d.nkp > 16) {
         fail(NULL, "too many [k]-indexed parameters");
@@ -709,6 +717,11 @@ static int launch_pass(chunk *h, int do_derivs, int do_back, int do_ls)
         p = timing_begin(h, TC_BACKPASS);
         h->o.bp_latency_build = h->bp_latency >= 0 ? h->bp_latency : (h->total_B <= 40000);
         h->o.cw_lpp = h->cw_lpp;
+        /* few problems on the GPU: four lanes per problem (a quarter of the matrix work per lane, box-QP iterations diverge over
+           8 problems instead of 32); threshold measured on B200 (scripts/gpu_probe_split.sh) */
+        h->o.bp_split = !h->d.bp_split_ok ? 0 : (h->bp_split >= 0 ? (h->bp_split == 4 ? 4 : 0) : (h->total_B <= BP_SPLIT_MAX_B ? 4 : 0));
+        h->o.bp_ppw = h->bp_ppw >= 1 ? h->bp_ppw : (h->o.bp_split ? 4 : 32);
+        if (h->o.bp_split && h->o.bp_ppw > 8) h->o.bp_ppw = 8;
         if (ilqgk_launch_backpass(&h->w, &h->o, h->params, h->iter, h->stream)) return failk(h);
         h->n_launches++;
         timing_end(h, p);
@@ -956,6 +969,11 @@ static long ck_get_int(chunk *h, const char *f, int *out)
     else if (!strcmp(f, "n_tails")) scal = w->n_tail;
     else if (!strcmp(f, "bp_done")) scal = w->bp_done;
     else if (!strcmp(f, "deriv_fail")) scal = w->deriv_fail;
+    if (!strcmp(f, "bp_split")) { /* lanes per problem the last backward pass of this chunk ran with (test hook) */
+        size_t b;
+        for (b = 0; b < B; b++) out[b] = h->o.bp_split;
+        return (long)B;
+    }
     if (scal) {
         if (ilqgk_d2h(out, scal, sizeof(int) * B, h->stream) || ilqgk_stream_sync(h->stream)) return failk(h);
         return (long)B;
@@ -1504,6 +1522,8 @@ int ilqgb_set_tuning(ilqgb_handle *h, const char *name, int value)
         if (!strcmp(name, "ls_tail_from")) h->c[i]->ls_tail_from = value;
         else if (!strcmp(name, "pass_index")) { h->c[i]->iter = value; h->c[i]->started = 1; }
         else if (!strcmp(name, "bp_latency")) h->c[i]->bp_latency = value;
+        else if (!strcmp(name, "bp_ppw") && value >= -1 && value <= 32 && value != 0) h->c[i]->bp_ppw = value;
+        else if (!strcmp(name, "bp_split") && (value == -1 || value == 0 || value == 4)) h->c[i]->bp_split = value;
         else if (!strcmp(name, "cw_lpp") && (value == 32 || value == 16 || value == 8)) h->c[i]->cw_lpp = value;
         else { snprintf(h->err, sizeof h->err, "unknown tuning knob"); return -1; }
     }

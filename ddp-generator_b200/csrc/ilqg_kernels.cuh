@@ -535,7 +535,11 @@ __global__ void __launch_bounds__(BP_BLOCK, MINB) k_backpass(Work w, Opts o, Par
     constexpr int NX = P::NX, NU = P::NU, NQXX = P::NQXX, NQUU = P::NQUU, NQXU = P::NQXU;
     constexpr int NF = bp_fields<P, FULL>();
     extern __shared__ double sm[];   /* 2 stages x NF fields x BP_BLOCK columns (dynamic: can exceed 48 KB) */
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    /* o.bp_ppw problems per warp (32 = every lane; fewer = the first lanes of more warps: when the batch does not fill the GPU,
+       a warp then serialises the divergent box-QP iterations of fewer problems) */
+    const int ppw = o.bp_ppw;
+    if ((int)(threadIdx.x & 31) >= ppw) return;
+    const int b = (blockIdx.x * (BP_BLOCK / 32) + (threadIdx.x >> 5)) * ppw + (threadIdx.x & 31);
     if (b >= w.B) return;
     if (w.status[b] != ST_RUNNING) return;
     ILQG_PARAMS(PP, b)
@@ -1225,6 +1229,10 @@ __global__ void __launch_bounds__(CW_WARPS * 32, (ILQG_CW_MINBLOCKS * LPP) / 32)
     w.lambda[b] = lambda;
     w.dlambda[b] = dlambda;
 }
+
+} /* namespace ilqg */
+#include "ilqg_backpass_split.cuh"
+namespace ilqg {
 
 /* =====================================================================================================================
  * K3: rollouts.  MODE 0 = initial rollout of the caller's controls (alpha = 0, clamped; iLQG_mex.c:113-120 and the

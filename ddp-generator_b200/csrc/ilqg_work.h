@@ -17,6 +17,9 @@ typedef struct ilqg_opts {
     int ls_tail_from;   /* line search: rounds [0, ls_tail_from) run one alpha per launch, the remaining alphas all at once;
                            >= n_alpha: purely sequential rounds (large batches) */
     int cw_lpp;         /* warp-cooperative backward pass: lanes per problem (32, 16 or 8; 32 / cw_lpp problems share a warp) */
+    int bp_split;       /* backward pass: lanes per problem of the small-batch kernel k_backpass_split (4), 0 = lane per problem */
+    int bp_ppw;         /* backward pass (lane per problem and split kernels): problems per warp; 32 (8 for the split kernel) = all
+                           lanes, fewer = sparse warps for small batches */
     int bp_single;      /* backward pass: 1 = one attempt at the current lambda, no retry, no exit test (back_pass(o) on its own) */
     int ls_commit_par;  /* 1: the tail records the state at the start of 32 time segments and the commit replays the
                            winner segment-parallel (one warp per problem); 0: the commit re-rolls the winner sequentially */

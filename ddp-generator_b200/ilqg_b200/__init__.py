@@ -21,7 +21,7 @@ LIB_DIR = os.environ.get("ILQG_LIB_DIR") or os.path.join(os.path.dirname(_HERE),
 TRACE, TIMING = 1, 2
 KERNEL_CLASSES = ("derivs", "backpass", "linesearch", "post")
 _SCALAR_FIELDS = {"cost", "new_cost", "dcost", "expected", "lambda", "dlambda", "g_norm", "dV0", "dV1", "w_pen_l", "w_pen_f",
-                  "iterations", "result", "status", "n_linesearch", "n_backpass", "n_derivs", "n_rollouts", "n_tails", "cur"}
+                  "iterations", "result", "status", "n_linesearch", "n_backpass", "n_derivs", "n_rollouts", "n_tails", "cur", "bp_split"}
 
 
 def lib_path(problem, full_ddp, lib_dir=None):
@@ -86,6 +86,7 @@ class Library:
         L.ilqgb_launch_count.restype = C.c_long
         L.ilqgb_launch_count.argtypes = [vp]
         L.ilqgb_chunks.argtypes = [vp]
+        L.ilqgb_set_tuning.argtypes = [vp, cp, ci]
         self.problem = L.ilqgb_problem_name().decode()
         self.nx, self.nu = L.ilqgb_nx(), L.ilqgb_nu()
         self.full_ddp = L.ilqgb_full_ddp()
@@ -228,6 +229,10 @@ class BatchSolver:
         it = np.empty(self.B, np.int32); res = np.empty(self.B, np.int32); nls = np.empty(self.B, np.int32)
         self._chk(self.lib.ilqgb_solve_host(self.h, _ptr(x0), _ptr(u0), _ptr(x), _ptr(u), _ptr(cost), _ptr(it), _ptr(res), _ptr(nls)))
         return dict(success=res, x=x, u=u, cost=cost, iterations=it, n_linesearch=nls)
+
+    def set_tuning(self, name, value):
+        """Run-time tuning knobs (ilqgb_set_tuning): ls_tail_from, bp_latency, bp_split, cw_lpp, pass_index."""
+        self._chk(self.lib.ilqgb_set_tuning(self.h, name.encode(), int(value)))
 
     def phase(self, which):
         self._chk(getattr(self.lib, f"ilqgb_phase_{which}")(self.h))

@@ -43,7 +43,7 @@ def oracle_record(kind, problem, ddp, T, params, x0, u0, opts, qp_cap=0):
     return rec
 
 
-def gpu_records(problem, ddp, T, params, x0, u0, opts, flags=1):
+def gpu_records(problem, ddp, T, params, x0, u0, opts, flags=1, tuning=None):
     """Solve a batch on the GPU; returns a list of per-problem records shaped like oracle_record()."""
     import ilqg_b200
 
@@ -55,6 +55,8 @@ def gpu_records(problem, ddp, T, params, x0, u0, opts, flags=1):
     s = ilqg_b200.BatchSolver(problem, ddp, B, T, flags=flags)
     s.set_options(opts)
     s.set_params(params)
+    for name, value in (tuning or {}).items():
+        s.set_tuning(name, value)
     out = s.solve(x0, u0)
     sc = {k: s.get(k) for k in ("lambda", "g_norm", "w_pen_l", "w_pen_f", "dV0", "dV1")}
     l, L = s.get("l"), s.get("L")
