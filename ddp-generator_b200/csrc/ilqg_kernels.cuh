@@ -809,6 +809,7 @@ template <class P> struct CoopWS {
     double ba[LX * P::NX], bc[LX * P::NU], bl[LU * P::NX], bv[P::NU];
     double Lk[P::NU * P::NX], lk[P::NU], invH[P::NQUU];
     double v2[P::NV2], c2[P::NC2];
+    double prod[(P::NT2XU + P::NT2UU + P::NT2XX) > 0 ? (P::NT2XU + P::NT2UU + P::NT2XX) : 1];   /* FULL_DDP: products Vx[i] * f??[i][entry], term order xu | uu | xx */
     int clamped[P::NU];
     unsigned char tri_r[P::NQXX], tri_c[P::NQXX];   /* packed upper-triangle index -> (row, col) */
 };
@@ -868,6 +869,58 @@ __global__ void __launch_bounds__(CW_WARPS * 32, (ILQG_CW_MINBLOCKS * LPP) / 32)
     }
     __syncwarp(gmask);
 
+    /* FULL_DDP tensor terms (back_pass.c:95-131: Q?? += sum_i Vx[i] * f??[i][entry]): the products of ALL terms are formed lane-parallel
+       in phase 1 (term t by lane t % LPP), then the lane that holds slot q of the list of entries that have terms adds its entry's
+       products in the reference's order -- one short round instead of a few lanes walking term lists while the others wait.
+       Loop-invariant descriptors: terms (index into Vx, source in v2 / c2) and entry slots (matrix, entry, term range). */
+    constexpr int NT2 = FULL ? (P::NT2XU + P::NT2UU + P::NT2XX) : 0, NE2 = FULL ? (P::NE2XU + P::NE2UU + P::NE2XX) : 0;
+    constexpr int RT = (NT2 + LPP - 1) / LPP, RS = (NE2 + LPP - 1) / LPP;
+    /* packed into one register each: term = Vx index | (source + 32768) << 8, -1 = none; slot = matrix (0 xu, 1 uu, 2 xx) | entry << 2 |
+       first term << 12 | end term << 22, -1 = none */
+    static_assert(NT2 < 512 && NQXX < 1024 && NQXU < 1024, "packed FULL_DDP descriptors");
+    int tdesc[RT > 0 ? RT : 1], sdesc[RS > 0 ? RS : 1];
+    if (FULL) {
+#pragma unroll
+        for (int r = 0; r < RT; r++) {
+            const int t = lane + LPP * r;
+            int vx = -1, src = 0;
+            if (t < P::NT2XU) { vx = P::s2xu_vx(t); src = P::s2xu_src(t); }
+            else if (t < P::NT2XU + P::NT2UU) { vx = P::s2uu_vx(t - P::NT2XU); src = P::s2uu_src(t - P::NT2XU); }
+            else if (t < NT2) { vx = P::s2xx_vx(t - P::NT2XU - P::NT2UU); src = P::s2xx_src(t - P::NT2XU - P::NT2UU); }
+            tdesc[r] = vx < 0 ? -1 : (vx | ((src + 32768) << 8));
+        }
+#pragma unroll
+        for (int r = 0; r < RS; r++) sdesc[r] = -1;
+        int cnt = 0;
+        for (int e = 0; e < NQXU; e++) {
+            const int t0 = P::s2xu_start(e), t1 = P::s2xu_start(e + 1);
+            if (t1 > t0) {
+#pragma unroll
+                for (int r = 0; r < RS; r++)
+                    if (cnt == lane + LPP * r) sdesc[r] = 0 | (e << 2) | (t0 << 12) | (t1 << 22);
+                cnt++;
+            }
+        }
+        for (int e = 0; e < NQUU; e++) {
+            const int t0 = P::s2uu_start(e), t1 = P::s2uu_start(e + 1);
+            if (t1 > t0) {
+#pragma unroll
+                for (int r = 0; r < RS; r++)
+                    if (cnt == lane + LPP * r) sdesc[r] = 1 | (e << 2) | ((t0 + P::NT2XU) << 12) | ((t1 + P::NT2XU) << 22);
+                cnt++;
+            }
+        }
+        for (int e = 0; e < NQXX; e++) {
+            const int t0 = P::s2xx_start(e), t1 = P::s2xx_start(e + 1);
+            if (t1 > t0) {
+#pragma unroll
+                for (int r = 0; r < RS; r++)
+                    if (cnt == lane + LPP * r) sdesc[r] = 2 | (e << 2) | ((t0 + P::NT2XU + P::NT2UU) << 12) | ((t1 + P::NT2XU + P::NT2UU) << 22);
+                cnt++;
+            }
+        }
+    }
+
     double dV0 = 0.0, dV1 = 0.0, g_sum = 0.0;
     int n_bp = w.n_bp[b];
     bool done = false;
@@ -919,6 +972,12 @@ __global__ void __launch_bounds__(CW_WARPS * 32, (ILQG_CW_MINBLOCKS * LPP) / 32)
                     if (j < P::NV2_USED) ws.v2[j] = pf2[t];
                 }
             }
+            double un[NU];   /* nominal control of step k (gradient measure at the end of the step): requested now, used ~4000 instructions later */
+            {
+                const double *unp = w.XU[cur] + ((size_t)k * Bp + b) * Rec<P>::RXU + NX;
+#pragma unroll
+                for (int i = 0; i < NU; i++) un[i] = unp[i];
+            }
             if (k > 0) {
                 const double *rec = w.V1 + ((size_t)(k - 1) * Bp + b) * P::NV1;
 #pragma unroll
@@ -963,25 +1022,22 @@ __global__ void __launch_bounds__(CW_WARPS * 32, (ILQG_CW_MINBLOCKS * LPP) / 32)
                 for (int s = 0; s < NX; s++) acc += ws.VxxF[r * LX + s] * ws.D.fx[s + c * NX];
                 ws.ba[r + c * LX] = acc;
             }
+            if (FULL) {
+#pragma unroll
+                for (int r = 0; r < RT; r++)
+                    if (tdesc[r] >= 0) {
+                        const int src = (tdesc[r] >> 8) - 32768;
+                        ws.prod[lane + LPP * r] = ws.Vx[tdesc[r] & 0xff] * (src >= 0 ? ws.v2[src] : ws.c2[-src - 1]);
+                    }
+            }
             __syncwarp(gmask);
-            /* ---- phase 2: Qxu, Quu, Qxx (+ FULL_DDP terms; same lane owns the same entry in both) ---- */
+            /* ---- phase 2: Qxu, Quu, Qxx (first-order parts; the FULL_DDP terms follow in phase 2b) ---- */
             for (int e = lane; e < NQXU; e += LPP) {
                 const int i = e % NX, j = e / NX;
                 double acc = 0.0;
 #pragma unroll
                 for (int s = 0; s < NX; s++) acc += ws.D.fx[s + i * NX] * ws.bc[s + j * LX];
                 double q = ws.D.cxu[e] + acc;
-                if (FULL) {
-                    const int t0 = P::s2xu_start(e), t1 = P::s2xu_start(e + 1);
-                    if (t1 > t0) {
-                        double d1 = 0.0;
-                        for (int t = t0; t < t1; t++) {
-                            const int src = P::s2xu_src(t);
-                            d1 += ws.Vx[P::s2xu_vx(t)] * (src >= 0 ? ws.v2[src] : ws.c2[-src - 1]);
-                        }
-                        q += d1;
-                    }
-                }
                 ws.Qxu[e] = q;
             }
             for (int e = lane; e < NQUU; e += LPP) {
@@ -995,17 +1051,6 @@ __global__ void __launch_bounds__(CW_WARPS * 32, (ILQG_CW_MINBLOCKS * LPP) / 32)
                     acc *= 0.5;
                 }
                 double q = ws.D.cuu[e] + acc;
-                if (FULL) {
-                    const int t0 = P::s2uu_start(e), t1 = P::s2uu_start(e + 1);
-                    if (t1 > t0) {
-                        double d1 = 0.0;
-                        for (int t = t0; t < t1; t++) {
-                            const int src = P::s2uu_src(t);
-                            d1 += ws.Vx[P::s2uu_vx(t)] * (src >= 0 ? ws.v2[src] : ws.c2[-src - 1]);
-                        }
-                        q += d1;
-                    }
-                }
                 ws.Quu[e] = q;
                 ws.QuuS[r * LU + c] = q;
                 ws.QuuS[c * LU + r] = q;
@@ -1021,20 +1066,29 @@ __global__ void __launch_bounds__(CW_WARPS * 32, (ILQG_CW_MINBLOCKS * LPP) / 32)
                     acc *= 0.5;
                 }
                 double q = ws.D.cxx[e] + acc;
-                if (FULL) {
-                    const int t0 = P::s2xx_start(e), t1 = P::s2xx_start(e + 1);
-                    if (t1 > t0) {
-                        double d1 = 0.0;
-                        for (int t = t0; t < t1; t++) {
-                            const int src = P::s2xx_src(t);
-                            d1 += ws.Vx[P::s2xx_vx(t)] * (src >= 0 ? ws.v2[src] : ws.c2[-src - 1]);
-                        }
-                        q += d1;
-                    }
-                }
                 ws.Qxx[e] = q;
             }
             __syncwarp(gmask);
+            if (FULL && NE2 > 0) {
+                /* ---- phase 2b: Q??[entry] += sum of its products, serial in the reference's term order ---- */
+#pragma unroll
+                for (int r = 0; r < RS; r++) {
+                    if (sdesc[r] < 0) continue;
+                    const int kind = sdesc[r] & 3, e = (sdesc[r] >> 2) & 1023, t1 = (sdesc[r] >> 22) & 1023;
+                    double d1 = 0.0;
+                    for (int t = (sdesc[r] >> 12) & 1023; t < t1; t++) d1 += ws.prod[t];
+                    if (kind == 0) ws.Qxu[e] += d1;
+                    else if (kind == 2) ws.Qxx[e] += d1;
+                    else {
+                        const int rr = ws.tri_r[e], cc = ws.tri_c[e];
+                        const double q = ws.Quu[e] + d1;
+                        ws.Quu[e] = q;
+                        ws.QuuS[rr * LU + cc] = q;
+                        ws.QuuS[cc * LU + rr] = q;
+                    }
+                }
+                __syncwarp(gmask);
+            }
             /* ---- regularisation (back_pass.c:134-159) ---- */
             for (int e = lane; e < NQUU; e += LPP) ws.QuuF[e] = ws.Quu[e];
             for (int e = lane; e < NQXU; e += LPP) ws.Qxu_reg[e] = ws.Qxu[e];
@@ -1189,7 +1243,6 @@ __global__ void __launch_bounds__(CW_WARPS * 32, (ILQG_CW_MINBLOCKS * LPP) / 32)
             }
             /* ---- gradient measure (back_pass.c:244-251) ---- */
             {
-                const double *un = w.XU[cur] + ((size_t)k * Bp + b) * Rec<P>::RXU + NX;
                 double gmax = 0.0;
 #pragma unroll
                 for (int i = 0; i < NU; i++) {

@@ -405,6 +405,9 @@ def emit_device(m, struct_name) -> str:
         o.append("    __device__ __forceinline__ static int s2%s_start(int j) { static constexpr unsigned short t[] = {%s}; return t[j]; }" % (nm, ", ".join(map(str, start))))
         o.append("    __device__ __forceinline__ static int s2%s_vx(int t_) { static constexpr unsigned char t[] = {%s}; return t[t_]; }" % (nm, ", ".join(map(str, vi + [0]))))
         o.append("    __device__ __forceinline__ static int s2%s_src(int t_) { static constexpr short t[] = {%s}; return t[t_]; }" % (nm, ", ".join(map(str, src + [0]))))
+        # number of terms / of output entries that have terms (the warp-cooperative kernel forms all products lane-parallel and
+        # sizes its per-lane term and entry slots from these)
+        o.append("    static constexpr int NT2%s = %d, NE2%s = %d;" % (nm.upper(), len(vi), nm.upper(), sum(1 for j in range(nout) if start[j + 1] > start[j])))
     o.append("    static constexpr int NC2 = %d;" % max(len(c2_slots), 1))
     for i, e in enumerate(c2_slots):
         sck2.out(("arr", "c2", i), e, False)
