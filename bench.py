@@ -376,11 +376,12 @@ def short_config(tag, problem, ddp, B, T, params, inputs, max_iter, sample_n, de
     n_ls_e2e = int(no.numpy().sum())
     same_e2e = bool(np.array_equal(cost_res, co.numpy()))
     chunks = S.chunks()
+    split = int(S.get_int("bp_split")[0])   # lanes per problem the backward pass ran with (4: k_backpass_split, small batches)
     S.close()
     n_k = max(1, B // chunks)
     kernels, kclocks, _ = kernels_alone(problem, ddp, n_k, T, params, x0_t.data_ptr(), u0_t.data_ptr(), max_iter, device, stream, nx, nu)
     dom = max(kernels, key=lambda k: kernels[k]["ms_total"])
-    names = {"derivs": "k_derivs", "backpass": "k_backpass_warp" if nx > 6 else "k_backpass", "linesearch": "k_ls_round"}
+    names = {"derivs": "k_derivs", "backpass": "k_backpass_warp" if nx > 6 else ("k_backpass_split" if split else "k_backpass"), "linesearch": "k_ls_round"}
     roof = roofline_of(kernels, dom, n_k, kclocks, names)
     if dom == "backpass":       # fp64-issue bound kernel: report it against the fp64 instruction peak, keep the HBM figure beside it
         f = kernels["backpass"]["fp64"]

@@ -73,8 +73,11 @@ template <int N, bool AL> __device__ __forceinline__ void sts_vec(double *p, con
     }
 }
 
+#ifndef ILQG_SP_MINBLOCKS
+#define ILQG_SP_MINBLOCKS 1
+#endif
 template <class P, bool PP, int G>
-__global__ void __launch_bounds__(SP_BLOCK) k_backpass_split(Work w, Opts o, ParamBlock<P> pb, int iter)
+__global__ void __launch_bounds__(SP_BLOCK, ILQG_SP_MINBLOCKS) k_backpass_split(Work w, Opts o, ParamBlock<P> pb, int iter)
 {
     static_assert(G == 2 || G == 4 || G == 8, "lanes per problem");
     static_assert(split_supported<P>(), "k_backpass_split: problem class not supported");
