@@ -9,8 +9,17 @@
  * the symmetric matrices are dealt round-robin -- while the short vectors the box QP needs (Qu, Quu) and the QP itself are
  * evaluated redundantly by every lane (identical inputs, identical results, uniform control flow inside a group).  The few
  * values another lane needs (columns of Vxx*fx, L, Quu*L, rows of Qxu, the new value function) travel through shared
- * memory, four group-level __syncwarp per step.  A warp-step is ~600 instructions, and QP iterations diverge over 8
- * problems instead of 32.
+ * memory, four group-level __syncwarp per step.  A warp-step is ~950 instructions (one lane per problem: ~1210), and the
+ * box-QP iterations of a warp diverge over 4 (default) or 8 problems instead of 32.
+ *
+ * Measured on B200 (car, 4096 problems, T = 500, 50 passes; ms per backward pass): one lane per problem 2.38 (0.95 in the
+ * first passes, 2.3-2.6 once a few lanes per warp iterate the box QP); this kernel with 8 problems per warp 1.88, with 4
+ * problems per warp 1.82, with 2 problems per warp 2.8 (more warps than the SMs hold at once).  Both kernels take the same
+ * 0.95 ms in the first passes: a step is one dependent chain of ~3700 cycles (about half of it the box QP: Cholesky, inverse
+ * and the Armijo test are serial divisions and square roots) that fewer instructions do not shorten, so the gain is the
+ * divergence.  The barriers name the four lanes of a group only: groups of a warp drift apart freely; a variant with
+ * warp-wide barriers (all groups forced back together four times per step) measured 7 % slower.  From ~8000 problems on
+ * the GPU the lane-per-problem kernel is as fast or faster (16 384: 2.4 against 3.9 ms), hence the threshold in ilqg_host.c.
  *
  * Parity: every output element is still ONE serial sum in the reference's order (matMult.c:3-72, back_pass.c:80-241), so the
  * results are bit-identical to k_backpass and to the reference.  The lane-owned products are evaluated densely (a lane's
@@ -73,11 +82,8 @@ template <int N, bool AL> __device__ __forceinline__ void sts_vec(double *p, con
     }
 }
 
-#ifndef ILQG_SP_MINBLOCKS
-#define ILQG_SP_MINBLOCKS 1
-#endif
 template <class P, bool PP, int G>
-__global__ void __launch_bounds__(SP_BLOCK, ILQG_SP_MINBLOCKS) k_backpass_split(Work w, Opts o, ParamBlock<P> pb, int iter)
+__global__ void __launch_bounds__(SP_BLOCK) k_backpass_split(Work w, Opts o, ParamBlock<P> pb, int iter)
 {
     static_assert(G == 2 || G == 4 || G == 8, "lanes per problem");
     static_assert(split_supported<P>(), "k_backpass_split: problem class not supported");
