@@ -809,6 +809,7 @@ template <class P> struct CoopWS {
     double ba[LX * P::NX], bc[LX * P::NU], bl[LU * P::NX], bv[P::NU];
     double Lk[P::NU * P::NX], lk[P::NU], invH[P::NQUU];
     double v2[P::NV2], c2[P::NC2];
+    double un[P::NU];   /* nominal control of the step (gradient measure), fetched one step ahead like the derivative entries */
     double prod[(P::NT2XU + P::NT2UU + P::NT2XX) > 0 ? (P::NT2XU + P::NT2UU + P::NT2XX) : 1];   /* FULL_DDP: products Vx[i] * f??[i][entry], term order xu | uu | xx */
     int clamped[P::NU];
     unsigned char tri_r[P::NQXX], tri_c[P::NQXX];   /* packed upper-triangle index -> (row, col) */
@@ -940,7 +941,8 @@ __global__ void __launch_bounds__(CW_WARPS * 32, (ILQG_CW_MINBLOCKS * LPP) / 32)
         for (int i = 0; i < NU; i++) lk[i] = 0.0;
         bool failed = false;
         constexpr int R1 = (P::NV1 + LPP - 1) / LPP, R2 = (P::NV2 + LPP - 1) / LPP;
-        double pf1[R1], pf2[R2];
+        constexpr int RU = (NU + LPP - 1) / LPP;
+        double pf1[R1], pf2[R2], pfu[RU];
         {
             const double *rec = w.V1 + ((size_t)(T - 1) * Bp + b) * P::NV1;
 #pragma unroll
@@ -953,6 +955,10 @@ __global__ void __launch_bounds__(CW_WARPS * 32, (ILQG_CW_MINBLOCKS * LPP) / 32)
             for (int t = 0; t < R2; t++) {
                 const int j = lane + LPP * t;
                 pf2[t] = (FULL && j < P::NV2_USED) ? rec2[j] : 0.0;
+            }
+            for (int t = 0; t < RU; t++) {
+                const int j = lane + LPP * t;
+                pfu[t] = (j < NU) ? w.XU[cur][((size_t)(T - 1) * Bp + b) * Rec<P>::RXU + NX + j] : 0.0;
             }
         }
 
@@ -972,13 +978,17 @@ __global__ void __launch_bounds__(CW_WARPS * 32, (ILQG_CW_MINBLOCKS * LPP) / 32)
                     if (j < P::NV2_USED) ws.v2[j] = pf2[t];
                 }
             }
-            double un[NU];   /* nominal control of step k (gradient measure at the end of the step): requested now, used ~4000 instructions later */
-            {
-                const double *unp = w.XU[cur] + ((size_t)k * Bp + b) * Rec<P>::RXU + NX;
 #pragma unroll
-                for (int i = 0; i < NU; i++) un[i] = unp[i];
+            for (int t = 0; t < RU; t++) {
+                const int j = lane + LPP * t;
+                if (j < NU) ws.un[j] = pfu[t];
             }
             if (k > 0) {
+#pragma unroll
+                for (int t = 0; t < RU; t++) {
+                    const int j = lane + LPP * t;
+                    if (j < NU) pfu[t] = w.XU[cur][((size_t)(k - 1) * Bp + b) * Rec<P>::RXU + NX + j];
+                }
                 const double *rec = w.V1 + ((size_t)(k - 1) * Bp + b) * P::NV1;
 #pragma unroll
                 for (int t = 0; t < R1; t++) {
@@ -1246,7 +1256,7 @@ __global__ void __launch_bounds__(CW_WARPS * 32, (ILQG_CW_MINBLOCKS * LPP) / 32)
                 double gmax = 0.0;
 #pragma unroll
                 for (int i = 0; i < NU; i++) {
-                    const double gi = fabs(lk[i]) / (fabs(un[i]) + 1.0);
+                    const double gi = fabs(lk[i]) / (fabs(ws.un[i]) + 1.0);
                     if (gi > gmax) gmax = gi;
                 }
                 g_sum += gmax;

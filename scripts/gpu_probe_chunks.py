@@ -6,6 +6,8 @@ sys.path.insert(0, os.path.join(ROOT, "ddp-generator_b200"))
 import ilqg_b200
 from ilqg_b200 import workloads as W
 ITERS = int(os.environ.get("ITERS", "50"))
+if os.environ.get("ILQG_LIB_DIR"):
+    ilqg_b200.LIB_DIR = os.environ["ILQG_LIB_DIR"]
 for B in [int(a) for a in sys.argv[1:]] or [4096]:
     x0, u0 = W.car_batch(B)
     for ch in [int(c) for c in os.environ.get("CHUNKSET", "1 2 4").split()]:
@@ -17,5 +19,9 @@ for B in [int(a) for a in sys.argv[1:]] or [4096]:
             s.upload(x0, u0); s.sync()
             t = time.perf_counter(); s.run(); s.sync(); best = min(best, time.perf_counter() - t)
         nls = s.download(False)["n_linesearch"].sum()
-        print(f"B={B} chunks={s.chunks()} split={s.get_int('bp_split')[0]}: {best*1e3:.1f} ms, {nls/best/1e6:.3f} M it/s, {best/ITERS*1e3:.3f} ms/pass", flush=True)
+        try:
+            split = s.get_int('bp_split')[0]
+        except Exception:
+            split = "?"
+        print(f"B={B} chunks={s.chunks()} split={split}: {best*1e3:.1f} ms, {nls/best/1e6:.3f} M it/s, {best/ITERS*1e3:.3f} ms/pass", flush=True)
         s.close()
