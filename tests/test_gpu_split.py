@@ -68,6 +68,20 @@ def test_problems_with_multipliers_split():
     both("brachi_hli", 120, params, x0[None], u0[None], opts)
 
 
+@pytest.mark.parametrize("tuning", [{"bp_split": 4, "bp_ppw": 8}, {"bp_split": 4, "bp_ppw": 2}, {"bp_split": 4, "bp_ppw": 1},
+                                     {"bp_split": 0, "bp_ppw": 16}, {"bp_split": 0, "bp_ppw": 3}, {"bp_split": 0, "bp_latency": 0, "bp_ppw": 8}])
+def test_problems_per_warp_do_not_change_results(tuning):
+    """Sparse warps (fewer problems per warp, both kernels, both register builds of k_backpass): the same records as the default."""
+    B, T = 21, 90
+    x0, u0 = W.car_batch(B, T=T, seed=19)
+    opts = {"max_iter": 30}
+    ref = PU.gpu_records("car", 0, T, W.CAR_PARAMS, x0, u0, opts, tuning={"bp_split": 0, "bp_ppw": 32})
+    got = PU.gpu_records("car", 0, T, W.CAR_PARAMS, x0, u0, opts, tuning=tuning)
+    for b in range(B):
+        for k in KEYS:
+            assert np.array_equal(np.asarray(ref[b][k]), np.asarray(got[b][k]), equal_nan=True), f"{tuning} b{b}: {k}"
+
+
 def test_split_is_the_default_for_small_batches_only():
     import ilqg_b200
 
