@@ -39,6 +39,7 @@ static ParamBlock<P> make_pb(const double *params)
 constexpr bool SPLIT_OK = (FULL_DDP == 0) && split_supported<P>();
 template <class Q, bool PP, bool OK> struct split_launcher {
     static void go(const ilqg_work *, const ilqg_opts *, const double *, int, void *) {}
+    static int preload() { return 0; }
 };
 template <class Q, bool PP> struct split_launcher<Q, PP, true> {
     static void go(const ilqg_work *w, const ilqg_opts *o, const double *params, int iter, void *stream)
@@ -51,11 +52,54 @@ template <class Q, bool PP> struct split_launcher<Q, PP, true> {
         const int ppw = o->bp_ppw < SP_BLOCK / 4 ? (o->bp_ppw < 1 ? 1 : o->bp_ppw) : SP_BLOCK / 4;
         k_backpass_split<Q, PP, 4><<<(unsigned)((w->B + ppw - 1) / ppw), SP_BLOCK, ssm, (cudaStream_t)stream>>>(*w, *o, pb, iter);
     }
+    static int preload()
+    {
+        cudaFuncAttributes a;
+        return cudaFuncGetAttributes(&a, k_backpass_split<Q, PP, 4>) == cudaSuccess ? 0 : -1;
+    }
 };
+
+/* CUDA loads a kernel lazily at its first launch, and a first launch in the middle of a solve stalls the running streams (measured:
+   the running-problem count of the solve engine, first launched in pass 9, cost a 115 ms solve 16 ms).  Every kernel a solve can
+   launch is therefore loaded when the first handle of a device is created: querying a function's attributes loads it. */
+template <class F> static int preload_one(F *f)
+{
+    cudaFuncAttributes a;
+    return cudaFuncGetAttributes(&a, f) == cudaSuccess ? 0 : -1;
+}
+template <bool PP> static int preload_pp()
+{
+    constexpr bool FULL = FULL_DDP != 0;
+    int bad = 0;
+    bad |= preload_one(k_init<P, PP>) | preload_one(k_rollout_only<P, PP>) | preload_one(k_derivs<P, FULL, PP>);
+    bad |= preload_one(k_ls_round<P, PP>) | preload_one(k_ls_tail<P, PP, true>) | preload_one(k_ls_tail<P, PP, false>);
+    bad |= preload_one(k_ls_commit_seg<P, PP>) | preload_one(k_ls_commit<P, PP, true>) | preload_one(k_ls_commit<P, PP, false>);
+    bad |= preload_one(k_post<P, PP>) | preload_one(k_mult<P, PP>) | preload_one(k_dense<P, PP>) | preload_one(k_clamp<P, PP>) | preload_one(k_eval<P, PP>);
+    if constexpr (use_coop<P>()) {
+        bad |= preload_one(k_backpass_warp<P, FULL, PP, 32>) | preload_one(k_backpass_warp<P, FULL, PP, 16>) | preload_one(k_backpass_warp<P, FULL, PP, 8>);
+    } else {
+        bad |= preload_one(k_backpass<P, FULL, 1, PP>) | preload_one(k_backpass<P, FULL, ILQG_BP_MINBLOCKS, PP>);
+    }
+    return bad;
+}
 
 extern "C" {
 
 const char *ilqgk_last_error(void) { return g_err; }
+
+int ilqgk_preload(void)
+{
+    static unsigned char loaded[ILQGK_MAX_DEVICES];
+    int dev = 0, bad = 0;
+    if (check(cudaGetDevice(&dev), "cudaGetDevice")) return -1;
+    if (dev >= 0 && dev < ILQGK_MAX_DEVICES && loaded[dev]) return 0;
+    bad |= preload_pp<false>() | preload_pp<true>();
+    bad |= split_launcher<P, false, SPLIT_OK>::preload() | split_launcher<P, true, SPLIT_OK>::preload();
+    bad |= preload_one(k_finalize) | preload_one(k_count_active) | preload_one(k_scatter) | preload_one(k_gather);
+    if (bad) { snprintf(g_err, sizeof g_err, "loading the kernels failed: %s", cudaGetErrorString(cudaGetLastError())); return -1; }
+    if (dev >= 0 && dev < ILQGK_MAX_DEVICES) loaded[dev] = 1;
+    return 0;
+}
 
 void ilqgk_dims(ilqgk_dims_t *d)
 {

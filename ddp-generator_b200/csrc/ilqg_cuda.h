@@ -19,6 +19,7 @@ int ilqgk_param_count(void);
 const char *ilqgk_param_name(int i);
 int ilqgk_param_size(int i);
 
+int ilqgk_preload(void); /* load every solver kernel on the current device (idempotent) */
 int ilqgk_device_count(void);
 int ilqgk_set_device(int dev);
 int ilqgk_malloc(void **p, size_t bytes);

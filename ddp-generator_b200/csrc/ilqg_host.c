@@ -369,6 +369,11 @@ static chunk *ck_create(int device, int batch, int n_hor, int flags, void *strea
     h->bp_split = env_int("ILQG_BP_SPLIT", -1);
     h->bp_ppw = env_int("ILQG_BP_PPW", -1);
     ilqgk_dims(&h->d);
+    if (ilqgk_set_device(device) || ilqgk_preload()) {   /* no lazily loaded kernel inside a later solve */
+        fail(NULL, ilqgk_last_error());
+        free(h);
+        return NULL;
+    }
     if (h->d.nkp > 16) {
         fail(NULL, "too many [k]-indexed parameters");
         free(h);

@@ -9,7 +9,7 @@ ITERS = int(os.environ.get("ITERS", "50"))
 if os.environ.get("ILQG_LIB_DIR"):
     ilqg_b200.LIB_DIR = os.environ["ILQG_LIB_DIR"]
 for B in [int(a) for a in sys.argv[1:]] or [4096]:
-    x0, u0 = W.car_batch(B)
+    x0, u0 = W.car_batch(B, first=int(os.environ.get("FIRST", "0")))
     for ch in [int(c) for c in os.environ.get("CHUNKSET", "1 2 4").split()]:
         s = ilqg_b200.BatchSolver("car", 0, B, 500, chunks=ch)
         s.set_params(W.CAR_PARAMS); s.set_options({"max_iter": 3}); s.upload(x0, u0); s.run(); s.sync()
