@@ -26,8 +26,8 @@
  * column is not known at compile time, so the structural-zero masks of k_backpass cannot prune them): exactly what the
  * reference does, i.e. the one documented deviation of k_backpass (non-finite x structural zero) does not occur here.
  *
- * Scope: FULL_DDP = 0, no state-dependent input limits (HAS_HX), lane-per-problem problems (not COOP); everything else keeps
- * using k_backpass / k_backpass_warp.  Reference: back_pass.c:38-257, boxQP.c:39-238, iLQG.c:261-303. */
+ * Scope: FULL_DDP = 0 and 1, no state-dependent input limits (HAS_HX), lane-per-problem problems (not COOP); everything else
+ * keeps using k_backpass / k_backpass_warp.  Reference: back_pass.c:38-257, boxQP.c:39-238, iLQG.c:261-303. */
 #pragma once
 
 namespace ilqg {
@@ -48,7 +48,8 @@ template <class P> struct SplitWS {
     static constexpr int OFF_BL = OFF_LK + ev(NU * NX);              /* Quu*L, column c at [c*NU] */
     static constexpr int OFF_QT = OFF_BL + ev(NU * NX);              /* Qxu transposed: row i of Qxu at [i*NU] */
     static constexpr int OFF_V = OFF_QT + ev(NU * NX);               /* new Vx | Vxx (packed upper triangle) */
-    static constexpr int RAW = OFF_V + ev(NX + P::NQXX);
+    static constexpr int OFF_V2 = OFF_V + ev(NX + P::NQXX);          /* FULL_DDP: time-varying second-order entries of the step */
+    static constexpr int RAW = OFF_V2 + ev(P::NV2);
     static constexpr int SIZE = RAW + (18 - RAW % 16);
 };
 
@@ -82,7 +83,7 @@ template <int N, bool AL> __device__ __forceinline__ void sts_vec(double *p, con
     }
 }
 
-template <class P, bool PP, int G>
+template <class P, bool FULL, bool PP, int G>
 __global__ void __launch_bounds__(SP_BLOCK) k_backpass_split(Work w, Opts o, ParamBlock<P> pb, int iter)
 {
     static_assert(G == 2 || G == 4 || G == 8, "lanes per problem");
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(SP_BLOCK) k_backpass_split(Work w, Opts o, Par
     constexpr int NOFF = NQXX - NX;                   /* off-diagonal entries of a symmetric NX x NX matrix */
     constexpr int ROUNDS = (NOFF + G - 1) / G;        /* off-diagonal entries per lane */
     constexpr int R1 = (P::NV1 + G - 1) / G;          /* time-varying derivative entries each lane fetches */
+    constexpr int NV2U = FULL ? P::NV2_USED : 0, R2 = (NV2U + G - 1) / G;   /* ... and second-order entries (FULL_DDP) */
     constexpr bool ALX = (NX % 2 == 0), ALU = (NU % 2 == 0);
     using WS = SplitWS<P>;
     static_assert(sizeof(Dense<P>) == sizeof(double) * P::DENSE_SIZE, "Dense layout must match the generator's table");
@@ -174,11 +176,14 @@ __global__ void __launch_bounds__(SP_BLOCK) k_backpass_split(Work w, Opts o, Par
         for (int i = 0; i < NU; i++) lk[i] = 0.0;
         bool failed = false;
         /* the entries of step k-1 are requested while step k is computed (registers pf / un_n) */
-        double pf[R1], un_n[NU];
+        double pf[R1], pf2[R2 > 0 ? R2 : 1], un_n[NU];
         {
             const double *v1 = w.V1 + (size_t)(T - 1) * P::NV1 * Bp + b;
 #pragma unroll
             for (int t = 0; t < R1; t++) pf[t] = dstv[t] ? v1[(size_t)(g + G * t) * Bp] : 0.0;
+            const double *v2g = w.V2 + (size_t)(T - 1) * P::NV2 * Bp + b;
+#pragma unroll
+            for (int t = 0; t < R2; t++) pf2[t] = (g + G * t) < NV2U ? v2g[(size_t)(g + G * t) * Bp] : 0.0;
             const double *un = w.XU[cur] + ((size_t)(T - 1) * Bp + b) * Rec<P>::RXU + NX;
 #pragma unroll
             for (int i = 0; i < NU; i++) un_n[i] = un[i];
@@ -189,6 +194,9 @@ __global__ void __launch_bounds__(SP_BLOCK) k_backpass_split(Work w, Opts o, Par
 #pragma unroll
             for (int t = 0; t < R1; t++)
                 if (dstv[t]) Dd[dst[t]] = pf[t];
+#pragma unroll
+            for (int t = 0; t < R2; t++)
+                if ((g + G * t) < NV2U) ws[WS::OFF_V2 + g + G * t] = pf2[t];
             double un[NU];
 #pragma unroll
             for (int i = 0; i < NU; i++) un[i] = un_n[i];
@@ -197,6 +205,10 @@ __global__ void __launch_bounds__(SP_BLOCK) k_backpass_split(Work w, Opts o, Par
 #pragma unroll
                 for (int t = 0; t < R1; t++)
                     if (dstv[t]) pf[t] = v1[(size_t)(g + G * t) * Bp];
+                const double *v2g = w.V2 + (size_t)(k - 1) * P::NV2 * Bp + b;
+#pragma unroll
+                for (int t = 0; t < R2; t++)
+                    if ((g + G * t) < NV2U) pf2[t] = v2g[(size_t)(g + G * t) * Bp];
                 const double *unp = w.XU[cur] + ((size_t)(k - 1) * Bp + b) * Rec<P>::RXU + NX;
 #pragma unroll
                 for (int i = 0; i < NU; i++) un_n[i] = unp[i];
@@ -290,6 +302,48 @@ __global__ void __launch_bounds__(SP_BLOCK) k_backpass_split(Work w, Opts o, Par
                 Qxx_o[t] = D.cxx[(c * (c + 1)) / 2 + r] + acc;
             }
 
+            if (FULL) {
+                /* ---- FULL_DDP tensor terms (back_pass.c:95-131): every lane evaluates the generated term sums of ALL entries into
+                        zeroed arrays (entries without terms stay literal zeros and fold away), then adds those of the entries it
+                        owns: Q = (first-order part) + sum, the order of the lane-per-problem kernel ---- */
+                double v2[P::NV2], tQxu[P::NQXU], tQuu[NQUU], tQxx[NQXX];
+#pragma unroll
+                for (int i = 0; i < P::NV2; i++) v2[i] = i < NV2U ? ws[WS::OFF_V2 + i] : 0.0;
+#pragma unroll
+                for (int i = 0; i < P::NQXU; i++) tQxu[i] = 0.0;
+#pragma unroll
+                for (int i = 0; i < NQUU; i++) tQuu[i] = 0.0;
+#pragma unroll
+                for (int i = 0; i < NQXX; i++) tQxx[i] = 0.0;
+                P::add2_Qxu(Vx, v2, pv, tQxu);
+                P::add2_Quu(Vx, v2, pv, tQuu);
+                P::add2_Qxx(Vx, v2, pv, tQxx);
+#pragma unroll
+                for (int i = 0; i < NQUU; i++) Quu[i] += tQuu[i];
+#pragma unroll
+                for (int t = 0; t < CPL; t++) {
+#pragma unroll
+                    for (int j = 0; j < NU; j++) {
+                        double d = 0.0;
+#pragma unroll
+                        for (int c = 0; c < NX; c++) d = (col[t] == c) ? tQxu[c + j * NX] : d;
+                        Qxu_c[t][j] += d;
+                    }
+                    double d = 0.0;
+#pragma unroll
+                    for (int c = 0; c < NX; c++) d = (col[t] == c) ? tQxx[utri(c, c)] : d;
+                    Qxx_d[t] += d;
+                }
+#pragma unroll
+                for (int t = 0; t < ROUNDS; t++) {
+                    double d = 0.0;
+#pragma unroll
+                    for (int c = 1; c < NX; c++)
+#pragma unroll
+                        for (int r = 0; r < c; r++) d = (ocol[t] == c && orow[t] == r) ? tQxx[utri(r, c)] : d;
+                    Qxx_o[t] += d;
+                }
+            }
             /* ---- regularisation (back_pass.c:134-159) ---- */
             double QuuF[NQUU], Qxu_reg[CPL][NU];
 #pragma unroll

@@ -34,9 +34,9 @@ static ParamBlock<P> make_pb(const double *params)
     return pb;
 }
 
-/* the small-batch backward pass exists for FULL_DDP = 0 problems without state-dependent input limits; the launcher is a class
+/* the small-batch backward pass exists for problems without state-dependent input limits; the launcher is a class
    template so that the kernel is only instantiated where it applies */
-constexpr bool SPLIT_OK = (FULL_DDP == 0) && split_supported<P>();
+constexpr bool SPLIT_OK = split_supported<P>();
 template <class Q, bool PP, bool OK> struct split_launcher {
     static void go(const ilqg_work *, const ilqg_opts *, const double *, int, void *) {}
     static int preload() { return 0; }
@@ -50,12 +50,12 @@ template <class Q, bool PP> struct split_launcher<Q, PP, true> {
         memset(&pb, 0, sizeof pb);
         memcpy(pb.v, params, sizeof(double) * Q::NPF_USED);
         const int ppw = o->bp_ppw < SP_BLOCK / 4 ? (o->bp_ppw < 1 ? 1 : o->bp_ppw) : SP_BLOCK / 4;
-        k_backpass_split<Q, PP, 4><<<(unsigned)((w->B + ppw - 1) / ppw), SP_BLOCK, ssm, (cudaStream_t)stream>>>(*w, *o, pb, iter);
+        k_backpass_split<Q, FULL_DDP != 0, PP, 4><<<(unsigned)((w->B + ppw - 1) / ppw), SP_BLOCK, ssm, (cudaStream_t)stream>>>(*w, *o, pb, iter);
     }
     static int preload()
     {
         cudaFuncAttributes a;
-        return cudaFuncGetAttributes(&a, k_backpass_split<Q, PP, 4>) == cudaSuccess ? 0 : -1;
+        return cudaFuncGetAttributes(&a, k_backpass_split<Q, FULL_DDP != 0, PP, 4>) == cudaSuccess ? 0 : -1;
     }
 };
 

@@ -124,8 +124,8 @@ int ilqgb_mod_chol(int device, int n, int count, const double *A, const double *
 int ilqgb_dense_size(void);
 /* run-time tuning knobs, otherwise chosen from the batch size: "ls_tail_from" (sequential line-search rounds before the
  * parallel-alpha tail; >= n_alpha: all rounds sequential, every tried rollout is stored as in the reference), "bp_latency";
- * "bp_split": lanes per problem of the backward pass, 4 = the small-batch kernel k_backpass_split (FULL_DDP = 0 problems without
- * state-dependent input limits; ignored otherwise), 0 = one lane per problem, -1 = by batch size; "cw_lpp";
+ * "bp_split": lanes per problem of the backward pass, 4 = the small-batch kernel k_backpass_split (problems without state-dependent input
+ * limits; ignored otherwise), 0 = one lane per problem, -1 = by batch size; "cw_lpp";
  * "pass_index": the loop index the next ilqgb_phase_* call runs as (row of the traces) */
 int ilqgb_set_tuning(ilqgb_handle *h, const char *name, int value);
 

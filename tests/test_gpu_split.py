@@ -15,12 +15,12 @@ KEYS = ("result", "iterations", "n_ls", "n_bp", "cost", "lambda", "g_norm", "w_p
         "tr_lambda", "tr_newcost", "tr_clamp", "x", "u", "l", "L")
 
 
-def both(problem, T, params, x0, u0, opts):
-    lane = PU.gpu_records(problem, 0, T, params, x0, u0, opts, tuning={"bp_split": 0})
-    split = PU.gpu_records(problem, 0, T, params, x0, u0, opts, tuning={"bp_split": 4})
+def both(problem, T, params, x0, u0, opts, ddp=0):
+    lane = PU.gpu_records(problem, ddp, T, params, x0, u0, opts, tuning={"bp_split": 0})
+    split = PU.gpu_records(problem, ddp, T, params, x0, u0, opts, tuning={"bp_split": 4})
     for b, (a, s) in enumerate(zip(lane, split)):
         for k in KEYS:
-            assert np.array_equal(np.asarray(a[k]), np.asarray(s[k]), equal_nan=True), f"{problem} b{b}: {k} differs between the kernels"
+            assert np.array_equal(np.asarray(a[k]), np.asarray(s[k]), equal_nan=True), f"{problem} ddp{ddp} b{b}: {k} differs between the kernels"
     return split
 
 
@@ -38,6 +38,19 @@ def test_car_split_equals_lane_and_oracle(opts):
         PU.assert_same(split[b], ora, f"car split b{b} vs {kind}", keys=PU.assert_same.__defaults__[0] + ("l", "L", "dV0", "dV1"))
 
 
+@pytest.mark.parametrize("opts", [{"max_iter": 45}, {"max_iter": 20, "regType": 2}, {"max_iter": 20, "lambdaInit": 1e-8, "lambdaMin": 1e-12}])
+def test_car_full_ddp_split_equals_lane_and_oracle(opts):
+    """FULL_DDP = 1: the second-order tensor terms (back_pass.c:95-131) through the split kernel; includes failed back passes
+    (the car with FULL_DDP needs the regularisation retries)."""
+    B, T = 21, 150
+    x0, u0 = W.car_batch(B, T=T, seed=13)
+    split = both("car", T, W.CAR_PARAMS, x0, u0, opts, ddp=1)
+    kind = PU.oracle_kinds("car", 1)[0]
+    for b in range(0, B, 4):
+        ora = PU.oracle_record(kind, "car", 1, T, W.CAR_PARAMS, x0[b], u0[b], opts)
+        PU.assert_same(split[b], ora, f"car ddp1 split b{b} vs {kind}", keys=PU.assert_same.__defaults__[0] + ("l", "L", "dV0", "dV1"))
+
+
 def test_car_full_horizon_split():
     """BASELINE config 3 subset through the split kernel, T = 500, max_iter = 50, against the oracle."""
     B = 24
@@ -50,22 +63,25 @@ def test_car_full_horizon_split():
         PU.assert_same(split[b], ora, f"car split b{b} vs {kind}")
 
 
+@pytest.mark.parametrize("ddp", [0, 1])
 @pytest.mark.parametrize("n", [2, 3, 5, 500])
-def test_brachistochrone_split(n):
-    """n_x = 3... state dimension below the lane count: lanes without a column of their own idle."""
+def test_brachistochrone_split(n, ddp):
+    """State dimension below the lane count: lanes without a column of their own idle."""
     params, x0, u0, opts = W.brachi(n)
-    split = both("brachi", n, params, x0[None], u0[None], opts)
-    for kind in PU.oracle_kinds("brachi", 0):
-        PU.assert_same(split[0], PU.oracle_record(kind, "brachi", 0, n, params, x0, u0, opts), f"brachi n={n} split vs {kind}")
+    split = both("brachi", n, params, x0[None], u0[None], opts, ddp=ddp)
+    for kind in PU.oracle_kinds("brachi", ddp):
+        PU.assert_same(split[0], PU.oracle_record(kind, "brachi", ddp, n, params, x0, u0, opts), f"brachi n={n} ddp{ddp} split vs {kind}")
 
 
 def test_problems_with_multipliers_split():
     """Augmented-Lagrangian problems (multipliers, penalty weights): pendulum (hle + hfi) and Brachistochrone with a running
     inequality; the failed solve of the pendulum set is included."""
     x0, u0 = W.pend_batch(9)
-    both("pend", W.PEND_T, W.PEND_PARAMS, x0, u0, W.PEND_OPTS)
+    for ddp in (0, 1):
+        both("pend", W.PEND_T, W.PEND_PARAMS, x0, u0, W.PEND_OPTS, ddp=ddp)
     params, x0, u0, opts = W.brachi_hli(120)
-    both("brachi_hli", 120, params, x0[None], u0[None], opts)
+    for ddp in (0, 1):
+        both("brachi_hli", 120, params, x0[None], u0[None], opts, ddp=ddp)
 
 
 @pytest.mark.parametrize("tuning", [{"bp_split": 4, "bp_ppw": 8}, {"bp_split": 4, "bp_ppw": 2}, {"bp_split": 4, "bp_ppw": 1},
