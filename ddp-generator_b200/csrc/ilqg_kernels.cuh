@@ -167,9 +167,15 @@ __device__ __forceinline__ double qp_value(const double *H, const double *g, con
     return val;
 }
 
-template <int M>
+/* CL > 0 (warp-cooperative callers, CL lanes hold identical QP state): the columns of the explicit inverse are computed by
+   different lanes -- lane c of the group solves the two triangular systems of column c, skipping by predicate the terms the
+   reference's loops start behind (i < col), then the columns are exchanged by shuffle.  Same operations in the same order
+   for every entry of the free block (checked on the host against the sequential form: bit-identical), 2M instead of
+   M(M+1) divisions per lane. */
+template <int M, int CL = 0>
 __device__ __forceinline__ int box_qp(const double *H, const double *g, const double *lower, const double *upper,
-                                      double *x, int *clamped, double *invH, int &n_free_out)
+                                      double *x, int *clamped, double *invH, int &n_free_out, int co_lane = 0, unsigned co_mask = 0u,
+                                      int co_base = 0)
 {
     constexpr int MP = (M * (M + 1)) / 2;
     const double min_grad = 1e-8, min_rel_improve = 1e-8, step_dec = 0.6, min_step = 1e-22, armijo = 0.1;
@@ -247,6 +253,34 @@ __device__ __forceinline__ int box_qp(const double *H, const double *g, const do
             if (!pd)
                 return -1;
             /* explicit inverse, one unit right-hand side per free column (cholesky.c:51-74), same scheme */
+            if (CL >= M && M > 2) {
+                const int col = co_lane < M ? co_lane : 0;
+                double wv[M];
+#pragma unroll
+                for (int k = 0; k < M; k++) {
+                    double wk = (k == col) ? 1.0 : 0.0;
+#pragma unroll
+                    for (int i = 0; i < k; i++) {
+                        const double t = wk - wv[i] * U[utri(i, k)];
+                        wk = (clamped[i] || i < col) ? wk : t;
+                    }
+                    wv[k] = wk / U[utri(k, k)];
+                }
+#pragma unroll
+                for (int k = M - 1; k >= 0; k--) {
+                    double wk = wv[k];
+#pragma unroll
+                    for (int i = k + 1; i < M; i++) {
+                        const double t = wk - wv[i] * U[utri(k, i)];
+                        wk = clamped[i] ? wk : t;
+                    }
+                    wv[k] = wk / U[utri(k, k)];
+                }
+#pragma unroll
+                for (int c = 0; c < M; c++)
+#pragma unroll
+                    for (int k = c; k < M; k++) invH[utri(c, k)] = __shfl_sync(co_mask, wv[k], co_base + c);
+            } else
 #pragma unroll
             for (int col = 0; col < M; col++) {
                 w[col] = 1.0;
@@ -1134,7 +1168,7 @@ __global__ void __launch_bounds__(CW_WARPS * 32, (ILQG_CW_MINBLOCKS * LPP) / 32)
                     lo[i] = ws.D.lower[i];
                     hi[i] = ws.D.upper[i];
                 }
-                qp = box_qp<NU>(H, g, lo, hi, lk, clamped, invH, n_free);
+                qp = box_qp<NU, LPP>(H, g, lo, hi, lk, clamped, invH, n_free, lane, gmask, (int)(threadIdx.x & 31) - lane);
             }
             if (lane == 0) {
                 if (w.tr_clamp) {
