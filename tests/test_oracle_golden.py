@@ -155,3 +155,15 @@ def test_setoptparam_messages():
         assert s.set_opt_raw(name, v) == msg, name
         if refs is not None:
             assert refs.set_opt_raw(name, v) == msg, name
+
+
+def test_inverse_columns_by_lane_equal_sequential_inverse(tmp_path):
+    """The warp-cooperative backward pass computes the columns of the box QP's explicit inverse in different lanes
+    (box_qp<M, CL> in csrc/ilqg_kernels.cuh); the restructured loops must give the reference's bits (cholesky.c:51-74)."""
+    import subprocess
+
+    exe = tmp_path / "inverse_columns_check"
+    src = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "inverse_columns_check.cpp")
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-o", str(exe), src], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout
